@@ -19,7 +19,7 @@ import numpy as np
 #  re-checked by tests/test_oracle_vs_reference.py when /root/reference is present)
 SHIPPED_MEAN_X = np.array([2.2073088909641334, 0.19405985835497927, 1.494994275926956])
 SHIPPED_SCALE_X = np.array([1.7144761363570307, 2.7973201512836416, 2.140079230865925])
-SHIPPED_MEAN_Y = np.array([0.05222916953218645, 0.9236331507819656, -1.3859332319838136,
+SHIPPED_MEAN_Y = np.array([0.052229169532186454, 0.9236331507819656, -1.3859332319838136,
                            -0.42092474514907724])
 SHIPPED_SCALE_Y = np.array([0.8768847052996848, 0.6520665510519178, 1.0214536342625566,
                             0.4481255851377674])
