@@ -9,7 +9,7 @@ ANN parity is UNPINNED (no real weights, no keras): ``mlp_predict`` restates the
 semantics of its third-party dependencies -- sklearn ``StandardScaler.transform`` =
 ``(X - mean_) / scale_`` in float64, Keras ``Dense`` = ``x @ kernel + bias`` with kernel shape
 (in, out) in float32, ``StandardScaler.inverse_transform`` = in-place ``X *= scale_; X += mean_``
-on the float32 prediction array (sklearn 1.0.2 per the pickles; keras/tensorflow unpinned,
+on the float32 prediction array (scale_/mean_ cast to float32 as current sklearn does) (sklearn 1.0.2 per the pickles; keras/tensorflow unpinned,
 reference Dockerfile:6).
 """
 import numpy as np
@@ -52,8 +52,10 @@ def mlp_predict(xyz, weights, biases, mean_x=SHIPPED_MEAN_X, scale_x=SHIPPED_SCA
         for W, b in zip(Ws[:-1], bs[:-1]):
             h = np.tanh(h @ W + b)                             # Dense(500, tanh)
         y = h @ Ws[-1] + bs[-1]                                # Dense(4), linear
-        y *= scale_y                                           # inverse_transform, in place on the
-        y += mean_y                                            # float32 array (two roundings)
+        y *= scale_y.astype(dtype)                             # inverse_transform, in place on the
+        y += mean_y.astype(dtype)                              # float32 array (sklearn >= 1.3 casts
+        #   scale_/mean_ to X.dtype first; 1.0.2 multiplied by the float64 vectors and rounded the
+        #   result -- a 1-ulp(fp32) difference, the reference's sklearn version is unpinned)
         out[lo:lo + chunk] = y
     return out
 

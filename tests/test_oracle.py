@@ -145,5 +145,5 @@ def test_shipped_scalers_match_constants():
     x = np.random.default_rng(1).uniform(-3, 6, size=(50, 3))
     np.testing.assert_array_equal(sx.transform(x), (x - sx.mean_) / sx.scale_)
     y = np.random.default_rng(2).normal(size=(50, 4)).astype(np.float32)
-    mine = y.copy(); mine *= sy.scale_; mine += sy.mean_
+    mine = y.copy(); mine *= sy.scale_.astype(np.float32); mine += sy.mean_.astype(np.float32)
     np.testing.assert_array_equal(sy.inverse_transform(y), mine)
