@@ -1,0 +1,410 @@
+// fabrik.cu -- K1: batched FABRIK inverse kinematics + fp64 angle extraction (sm_100a).
+//
+// Replaces, per target, reference FabrikInverseKinematics.ikine (inverse.py:115-139):
+//   check_limits (inverse.py:26-35) -> Fabrik.calculate (fabrik.py:44-67, built from
+//   get_point_between / get_distance_between, point.py:25-45) -> __get_angles (inverse.py:54-112).
+//
+// Design (see DESIGN.md "K1"):
+//  * One chain per lane, chain state in registers.  The seed chain and the target lie in one
+//    vertical plane through the z axis, so the iteration runs in 2-D (r, z) coordinates.
+//  * P0 is pinned to the start joint and P3 is only needed at the end, so one iteration is
+//    4 point-at-distance updates + 5 reciprocal square roots; the two convergence errors are
+//    | |S - b1| - d0 | and | |T - f2| - d3 | (algebraically the reference's |b0 - S|, |f3 - T|).
+//  * Iteration counts are bimodal (3..8 inside the workspace, exactly max_iter outside), so lanes
+//    are REFILLED: a lane that converges parks its chain in a per-warp shared-memory queue and
+//    takes the next target from a pre-staged input queue; the expensive fp64 epilogue (8 sqrt,
+//    3 acos, atan2) runs only when 32 parked chains are available, i.e. always at full warp width.
+//  * Work is handed out in chunks of IKB_FABRIK_CHUNK consecutive targets from a global counter
+//    (persistent warps, no tail imbalance); row i of the output always belongs to row i of the input.
+#include "ikb_common.cuh"
+
+#define IKB_FABRIK_CHUNK 256
+#define IKB_FABRIK_WARPS 8
+#define IKB_Q 64  // per-warp queue capacity (ring), power of two
+
+namespace {
+
+struct FabrikArgs {
+    const void *xyz;
+    int xyz_f64;
+    long long n;
+    long long index_base;  // global row of xyz[0] (host pipeline chunks)
+    void *angles;
+    int angles_f64;
+    int *iters;  // nullable
+    IkbDeviceStats *stats;
+    unsigned long long *work_counter;
+    IkbRobot rc;
+};
+
+template <typename Real>
+struct PlanarChain {
+    Real r1, z1, r2, z2;  // joints 1 and 2; joint 0 is pinned, joint 3 is derived
+};
+
+// One forward-and-backward-reaching pass (reference fabrik.py:60-63) in the (r, z) plane.
+// Returns true when the reference's loop condition (start_error > tol or goal_error > tol) holds.
+template <typename Real>
+__device__ __forceinline__ bool fabrik_pass(PlanarChain<Real> &c, Real Tr, Real Tz, Real R0, Real Z0,
+                                            Real d0, Real d1, Real d2, Real d3, Real tol)
+{
+    // backward (fabrik.py:19-29): b3 = T, b2 = PB(b3, P2, d2), b1 = PB(b2, P1, d1), b0 = PB(b1, P0, d0)
+    Real dr = c.r2 - Tr, dz = c.z2 - Tz;
+    Real s = d2 * ikb_rsqrt(dr * dr + dz * dz);
+    Real b2r = Tr + s * dr, b2z = Tz + s * dz;
+    dr = c.r1 - b2r; dz = c.z1 - b2z;
+    s = d1 * ikb_rsqrt(dr * dr + dz * dz);
+    Real b1r = b2r + s * dr, b1z = b2z + s * dz;
+    dr = R0 - b1r; dz = Z0 - b1z;
+    Real n2 = dr * dr + dz * dz;
+    Real rs = ikb_rsqrt(n2);
+    Real se = fabs(n2 * rs - d0);  // |b0 - S| = | |S - b1| - d0 |            (fabrik.py:61)
+    // forward (fabrik.py:32-42): f0 = S, f1 = PB(f0, b1, d1), f2 = PB(f1, b2, d2), f3 = PB(f2, b3, d3)
+    s = d1 * rs;
+    c.r1 = R0 - s * dr; c.z1 = Z0 - s * dz;  // (b1 - S) = -(dr, dz)
+    dr = b2r - c.r1; dz = b2z - c.z1;
+    s = d2 * ikb_rsqrt(dr * dr + dz * dz);
+    c.r2 = c.r1 + s * dr; c.z2 = c.z1 + s * dz;
+    dr = Tr - c.r2; dz = Tz - c.z2;
+    n2 = dr * dr + dz * dz;
+    Real ge = fabs(n2 * ikb_rsqrt(n2) - d3);  // |f3 - T| = | |T - f2| - d3 |   (fabrik.py:63)
+    return (se > tol) | (ge > tol);
+}
+
+__device__ __forceinline__ double dist2d(double ar, double az, double br, double bz)
+{
+    double dr = ar - br, dz = az - bz;
+    return sqrt(dr * dr + dz * dz);
+}
+
+// round(x, 8) of reference inverse.py:81,92,100 (np.round-style rint(x * 1e8) / 1e8)
+__device__ __forceinline__ double round8(double x) { return rint(x * 1e8) / 1e8; }
+
+// Finish one solved chain: derive the effector, lift to 3-D, extract the four angles in fp64
+// exactly as reference inverse.py:54-112 does, write outputs, raise the per-row flags.
+__device__ __forceinline__ void fabrik_epilogue(const FabrikArgs &a, int idx, int k, double r1,
+                                                double z1, double r2, double z2)
+{
+    const IkbRobot &rc = a.rc;
+    const double PI = 3.141592653589793;
+    double x, y, z;
+    ikb_load_xyz(a.xyz, a.xyz_f64, idx, x, y, z);
+    const long long row = a.index_base + idx;
+    if (ikb_out_of_limits(rc, x, y, z))
+        atomicMin(&a.stats->first_out_of_limits, row);
+    const double Tr = sqrt(x * x + y * y), Tz = z;
+    const double R0 = rc.seed_r[0], Z0 = rc.seed_z[0];
+    double r3, z3;
+    bool zero_div = false;
+    if (k == 0) {  // the reference's loop never ran: the chain is the seed chain
+        r1 = rc.seed_r[1]; z1 = rc.seed_z[1]; r2 = rc.seed_r[2]; z2 = rc.seed_z[2];
+        r3 = rc.seed_r[3]; z3 = rc.seed_z[3];
+    } else {       // f3 = PB(f2, T, d3) (fabrik.py:40)
+        double dr = Tr - r2, dz = Tz - z2;
+        double n = sqrt(dr * dr + dz * dz);
+        zero_div |= (n == 0.0);
+        double s = rc.links[3] / n;
+        r3 = r2 + s * dr; z3 = z2 + s * dz;
+    }
+    // a NaN chain from finite input can only come from 0 * inf, i.e. a zero-length segment
+    const bool finite_in = isfinite(x) & isfinite(y) & isfinite(z);
+    zero_div |= finite_in & !(isfinite(r1) & isfinite(z1) & isfinite(r2) & isfinite(z2));
+    // horizontal direction of the solve plane; targets on the z axis have no direction (the
+    // reference's theta_1 is rounding noise there): use +x.
+    const double ux = Tr > 0.0 ? x / Tr : 1.0, uy = Tr > 0.0 ? y / Tr : 0.0;
+    double th[4];
+    th[0] = atan2(r3 * uy, r3 * ux);                                    // inverse.py:60
+    const double ab = sqrt(R0 * R0 + Z0 * Z0);                           // A = origin
+    const double bc = dist2d(R0, Z0, r1, z1), cd = dist2d(r1, z1, r2, z2);
+    const double de = dist2d(r2, z2, r3, z3);
+    const double ac = sqrt(r1 * r1 + z1 * z1);
+    const double bd = dist2d(R0, Z0, r2, z2), ce = dist2d(r1, z1, r3, z3);
+    double den = 2 * ab * bc;
+    zero_div |= (den == 0.0);
+    const double c2 = round8((ab * ab + bc * bc - ac * ac) / den);       // inverse.py:77-81
+    const double acos2 = acos(c2);
+    th[1] = ((r1 * ux) * (r2 * ux) < 0) ? (3 * PI / 2) - acos2 : -(PI / 2 - acos2);  // :82-85
+    den = 2 * bc * cd;
+    zero_div |= (den == 0.0);
+    const double c3 = round8((bc * bc + cd * cd - bd * bd) / den);       // :90-92
+    th[2] = -(PI - acos(c3));                                            // :93
+    den = 2 * cd * de;
+    zero_div |= (den == 0.0) | (ce == 0.0);
+    const double c4 = round8((cd * cd + de * de - ce * ce) / den);       // :98-100
+    const double acos4 = acos(c4);
+    // t4_point_bt = PB(C, E, |CE| / 2) (inverse.py:102): (|CE|/2)/|CE| is exactly 0.5
+    const double mr = r1 + 0.5 * (r3 - r1), mz = z1 + 0.5 * (z3 - z1);
+    const double dista = dist2d(R0, Z0, mr, mz);
+    th[3] = (bd > dista) ? -(PI - acos4) : (PI - acos4);                 // :103-108
+    const bool domain = !zero_div & (fabs(c2) > 1.0 | fabs(c3) > 1.0 | fabs(c4) > 1.0);
+    if (zero_div) {
+        th[0] = th[1] = th[2] = th[3] = __longlong_as_double(0x7ff8000000000000LL);
+        atomicMin(&a.stats->first_zero_division, row);
+    }
+    if (domain)
+        atomicMin(&a.stats->first_domain_error, row);
+    ikb_store_angles(a.angles, a.angles_f64, idx, th);
+    if (a.iters)
+        a.iters[idx] = k;
+}
+
+template <typename Real>
+__global__ void __launch_bounds__(IKB_FABRIK_WARPS * 32, 3) fabrik_planar_kernel(const FabrikArgs a)
+{
+    // per-warp rings: input queue (pre-staged targets) and output queue (parked solved chains)
+    __shared__ int s_in_idx[IKB_FABRIK_WARPS][IKB_Q];
+    __shared__ Real s_in_tr[IKB_FABRIK_WARPS][IKB_Q];
+    __shared__ Real s_in_tz[IKB_FABRIK_WARPS][IKB_Q];
+    __shared__ int s_out_idx[IKB_FABRIK_WARPS][IKB_Q];
+    __shared__ int s_out_k[IKB_FABRIK_WARPS][IKB_Q];
+    __shared__ Real s_out_c[IKB_FABRIK_WARPS][4][IKB_Q];
+
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const unsigned lt = ikb_lanemask_lt();
+    const IkbRobot &rc = a.rc;
+    const Real R0 = (Real)rc.seed_r[0], Z0 = (Real)rc.seed_z[0];
+    const Real d0 = (Real)rc.links[0], d1 = (Real)rc.links[1], d2 = (Real)rc.links[2],
+               d3 = (Real)rc.links[3], tol = (Real)rc.tol;
+    const int max_iter = rc.max_iter;
+
+    bool active = false, exhausted = false;
+    int idx = 0, k = 0;
+    Real Tr = 0, Tz = 0;
+    PlanarChain<Real> c{0, 0, 0, 0};
+    long long cur = 0, cur_end = 0;
+    int in_head = 0, in_cnt = 0, out_head = 0, out_cnt = 0;
+    unsigned long long iters_local = 0;
+    unsigned solved_local = 0, capped_local = 0;
+
+    for (;;) {
+        // 1. top up the input queue, one coalesced full-warp load of up to 32 targets
+        if (in_cnt <= 32 && !exhausted) {
+            if (cur == cur_end) {
+                unsigned long long base = 0;
+                if (lane == 0)
+                    base = atomicAdd(a.work_counter, (unsigned long long)IKB_FABRIK_CHUNK);
+                base = __shfl_sync(IKB_FULL_MASK, base, 0);
+                if ((long long)base >= a.n) {
+                    exhausted = true;
+                } else {
+                    cur = (long long)base;
+                    cur_end = min(cur + IKB_FABRIK_CHUNK, a.n);
+                }
+            }
+            if (!exhausted) {
+                const int m = (int)min((long long)32, cur_end - cur);
+                if (lane < m) {
+                    double x, y, z;
+                    ikb_load_xyz(a.xyz, a.xyz_f64, cur + lane, x, y, z);
+                    const int slot = (in_head + in_cnt + lane) & (IKB_Q - 1);
+                    s_in_idx[w][slot] = (int)(cur + lane);
+                    s_in_tr[w][slot] = (Real)sqrt(x * x + y * y);
+                    s_in_tz[w][slot] = (Real)z;
+                }
+                in_cnt += m;
+                cur += m;
+                __syncwarp();
+            }
+        }
+        // 2. idle lanes take the next staged targets
+        const unsigned need = __ballot_sync(IKB_FULL_MASK, !active);
+        if (need != 0 && in_cnt > 0) {
+            const int rank = __popc(need & lt);
+            if (!active && rank < in_cnt) {
+                const int slot = (in_head + rank) & (IKB_Q - 1);
+                idx = s_in_idx[w][slot];
+                Tr = s_in_tr[w][slot];
+                Tz = s_in_tz[w][slot];
+                c.r1 = (Real)rc.seed_r[1]; c.z1 = (Real)rc.seed_z[1];
+                c.r2 = (Real)rc.seed_r[2]; c.z2 = (Real)rc.seed_z[2];
+                k = 0;
+                active = true;
+            }
+            const int take = min(__popc(need), in_cnt);
+            in_head = (in_head + take) & (IKB_Q - 1);
+            in_cnt -= take;
+            __syncwarp();
+        }
+        if (__ballot_sync(IKB_FULL_MASK, active) == 0) {
+            if (exhausted && in_cnt == 0)
+                break;
+            continue;
+        }
+        // 3. one FABRIK pass for every active lane (reference fabrik.py:57-65)
+        bool done = false;
+        if (active) {
+            if (rc.zero_iter) {
+                done = true;
+            } else {
+                const bool more = fabrik_pass(c, Tr, Tz, R0, Z0, d0, d1, d2, d3, tol);
+                ++k;
+                done = !more | (k >= max_iter);
+                if (done)
+                    capped_local += (more ? 1u : 0u);
+            }
+        }
+        // 4. park finished chains; run the epilogue once a full warp of them is waiting
+        const unsigned fin = __ballot_sync(IKB_FULL_MASK, done);
+        if (fin != 0) {
+            if (done) {
+                const int slot = (out_head + out_cnt + __popc(fin & lt)) & (IKB_Q - 1);
+                s_out_idx[w][slot] = idx;
+                s_out_k[w][slot] = k;
+                s_out_c[w][0][slot] = c.r1; s_out_c[w][1][slot] = c.z1;
+                s_out_c[w][2][slot] = c.r2; s_out_c[w][3][slot] = c.z2;
+                iters_local += (unsigned)k;
+                ++solved_local;
+                active = false;
+            }
+            out_cnt += __popc(fin);
+            __syncwarp();
+            if (out_cnt >= 32) {
+                const int slot = (out_head + lane) & (IKB_Q - 1);
+                fabrik_epilogue(a, s_out_idx[w][slot], s_out_k[w][slot], (double)s_out_c[w][0][slot],
+                                (double)s_out_c[w][1][slot], (double)s_out_c[w][2][slot],
+                                (double)s_out_c[w][3][slot]);
+                out_head = (out_head + 32) & (IKB_Q - 1);
+                out_cnt -= 32;
+                __syncwarp();
+            }
+        }
+    }
+    // drain the parked chains that never filled a whole warp
+    if (lane < out_cnt) {
+        const int slot = (out_head + lane) & (IKB_Q - 1);
+        fabrik_epilogue(a, s_out_idx[w][slot], s_out_k[w][slot], (double)s_out_c[w][0][slot],
+                        (double)s_out_c[w][1][slot], (double)s_out_c[w][2][slot],
+                        (double)s_out_c[w][3][slot]);
+    }
+    // statistics: one atomic per warp and counter
+    const unsigned long long it = ikb_warp_sum(iters_local);
+    const unsigned sv = ikb_warp_sum(solved_local), cp = ikb_warp_sum(capped_local);
+    if (lane == 0 && sv != 0) {
+        atomicAdd(&a.stats->sum_iterations, it);
+        atomicAdd(&a.stats->n_solved, (unsigned long long)sv);
+        if (cp)
+            atomicAdd(&a.stats->n_iter_capped, (unsigned long long)cp);
+    }
+}
+
+// ---- generic 3-D path ---------------------------------------------------------------------------
+// IEEE fp64 with the reference's operation order (point.py:25-45): correctly rounded sqrt and
+// division, explicit _rn intrinsics so nothing is contracted into FMAs.  One chain per thread.
+struct Vec3 {
+    double x, y, z;
+};
+
+__device__ __forceinline__ double dist3(const Vec3 &a, const Vec3 &b)
+{
+    const double dx = __dsub_rn(a.x, b.x), dy = __dsub_rn(a.y, b.y), dz = __dsub_rn(a.z, b.z);
+    return __dsqrt_rn(__dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz)));
+}
+
+// get_point_between(s, e, L) = s + (L / |s - e|) * (e - s); NaN when the distance is 0
+__device__ __forceinline__ Vec3 point_between3(const Vec3 &s, const Vec3 &e, double L)
+{
+    const double t = __ddiv_rn(L, dist3(s, e));
+    Vec3 o;
+    o.x = __dadd_rn(s.x, __dmul_rn(t, __dsub_rn(e.x, s.x)));
+    o.y = __dadd_rn(s.y, __dmul_rn(t, __dsub_rn(e.y, s.y)));
+    o.z = __dadd_rn(s.z, __dmul_rn(t, __dsub_rn(e.z, s.z)));
+    return o;
+}
+
+struct FabrikGenericArgs {
+    const double *init;  // n_init x 4 x 3
+    long long n_init;
+    const double *goals;  // n x 3
+    long long n;
+    double *chain_out;  // n x 4 x 3
+    int *iters;         // nullable
+    IkbDeviceStats *stats;
+    IkbRobot rc;
+};
+
+__global__ void __launch_bounds__(128) fabrik_generic_kernel(const FabrikGenericArgs a)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.n)
+        return;
+    const double *ip = a.init + (a.n_init == 1 ? 0 : 12 * i);
+    Vec3 P[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+        P[j] = Vec3{ip[3 * j], ip[3 * j + 1], ip[3 * j + 2]};
+    const Vec3 S = P[0];
+    const Vec3 T{a.goals[3 * i], a.goals[3 * i + 1], a.goals[3 * i + 2]};
+    const double *d = a.rc.links;
+    const double tol = a.rc.tol;
+    double se = 1.0, ge = 1.0;
+    int step = 0;
+    while ((se > tol || ge > tol) && a.rc.max_iter > step) {  // fabrik.py:57-59
+        const Vec3 b2 = point_between3(T, P[2], d[2]);
+        const Vec3 b1 = point_between3(b2, P[1], d[1]);
+        const Vec3 b0 = point_between3(b1, P[0], d[0]);
+        se = dist3(b0, S);
+        P[0] = S;
+        P[1] = point_between3(P[0], b1, d[1]);
+        P[2] = point_between3(P[1], b2, d[2]);
+        P[3] = point_between3(P[2], T, d[3]);
+        ge = dist3(P[3], T);
+        ++step;
+    }
+    bool nan_out = false;
+    double *o = a.chain_out + 12 * i;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        o[3 * j] = P[j].x; o[3 * j + 1] = P[j].y; o[3 * j + 2] = P[j].z;
+        nan_out |= !(isfinite(P[j].x) & isfinite(P[j].y) & isfinite(P[j].z));
+    }
+    if (a.iters)
+        a.iters[i] = step;
+    if (nan_out && isfinite(T.x) && isfinite(T.y) && isfinite(T.z))
+        atomicMin(&a.stats->first_zero_division, i);
+    atomicAdd(&a.stats->sum_iterations, (unsigned long long)step);
+    atomicAdd(&a.stats->n_solved, 1ULL);
+}
+
+}  // namespace
+
+// ---- launchers (called from capi.cu) --------------------------------------------------------------
+cudaError_t ikb_launch_fabrik_planar(const void *xyz, int xyz_f64, long long n, long long index_base,
+                                     void *angles, int angles_f64, int *iters, int precision,
+                                     IkbDeviceStats *stats, unsigned long long *work_counter,
+                                     const IkbRobot &rc, int num_sms, cudaStream_t stream)
+{
+    if (n <= 0)
+        return cudaSuccess;
+    FabrikArgs a;
+    a.xyz = xyz; a.xyz_f64 = xyz_f64; a.n = n; a.index_base = index_base;
+    a.angles = angles; a.angles_f64 = angles_f64; a.iters = iters;
+    a.stats = stats; a.work_counter = work_counter; a.rc = rc;
+    cudaError_t err = cudaMemsetAsync(work_counter, 0, sizeof(unsigned long long), stream);
+    if (err != cudaSuccess)
+        return err;
+    // persistent grid: resident CTAs per SM x SM count, trimmed for small batches
+    const int per_cta = IKB_FABRIK_WARPS * 32;
+    long long want = (n + per_cta - 1) / per_cta;
+    long long grid = (long long)num_sms * 3;
+    if (want < grid)
+        grid = want;
+    if (precision == IKB_FABRIK_F32)
+        fabrik_planar_kernel<float><<<(unsigned)grid, per_cta, 0, stream>>>(a);
+    else
+        fabrik_planar_kernel<double><<<(unsigned)grid, per_cta, 0, stream>>>(a);
+    return cudaGetLastError();
+}
+
+cudaError_t ikb_launch_fabrik_generic(const double *init, long long n_init, const double *goals,
+                                      long long n, double *chain_out, int *iters,
+                                      IkbDeviceStats *stats, const IkbRobot &rc, cudaStream_t stream)
+{
+    if (n <= 0)
+        return cudaSuccess;
+    FabrikGenericArgs a;
+    a.init = init; a.n_init = n_init; a.goals = goals; a.n = n; a.chain_out = chain_out;
+    a.iters = iters; a.stats = stats; a.rc = rc;
+    const unsigned grid = (unsigned)((n + 127) / 128);
+    fabrik_generic_kernel<<<grid, 128, 0, stream>>>(a);
+    return cudaGetLastError();
+}

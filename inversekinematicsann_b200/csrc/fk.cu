@@ -1,0 +1,274 @@
+// fk.cu -- K0 (workspace-limit check), K3 (batched DH forward kinematics / position error) and the
+// FMA-pipe microbenchmark (sm_100a).
+//
+// K3 replaces reference ForwardKinematics.fkine (forward.py:73-94) for batches:
+//   T = prod_i Rz(theta_i) Tz(eps_i) Tx(a_i) Rx(alpha_i)                      (forward.py:62-70)
+// Only what callers read is produced in the batched form -- the end-effector position T[0:3, 3]
+// (cli.py:60, inverse.py:130, tests/forward_unit.py:30) and ||pos - target||.  The chain kernel
+// returns all four cumulative 4x4 matrices for the (T, [T1..T4]) return value of fkine.
+// HBM-bound: 16 B angles + 12 B target in, 4 B error out per row (fp32 buffers).
+#include "ikb_common.cuh"
+
+namespace {
+
+__device__ __forceinline__ void ikb_sincos(float x, float *s, float *c) { sincosf(x, s, c); }
+__device__ __forceinline__ void ikb_sincos(double x, double *s, double *c) { sincos(x, s, c); }
+
+// Position-only DH chain: p += R [a c, a s, eps]; R = R Rz(theta) Rx(alpha).
+template <typename Real>
+__device__ __forceinline__ bool fk_position(const IkbRobot &rc, const Real th[4], Real &px, Real &py,
+                                            Real &pz)
+{
+    const Real TWO_PI = (Real)6.283185307179586;
+    Real R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+    px = py = pz = 0;
+    bool ok = true;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const Real t = th[i];
+        ok &= !(t < -TWO_PI) & !(t > TWO_PI);  // forward.py:23-25 (NaN passes, as upstream)
+        Real s, c;
+        ikb_sincos(t, &s, &c);
+        const Real a = (Real)rc.a[i], e = (Real)rc.eps[i];
+        const Real vx = a * c, vy = a * s;
+        px += R[0] * vx + R[1] * vy + R[2] * e;
+        py += R[3] * vx + R[4] * vy + R[5] * e;
+        pz += R[6] * vx + R[7] * vy + R[8] * e;
+        if (i < 3) {
+            const Real ca = (Real)rc.cos_alpha[i], sa = (Real)rc.sin_alpha[i];
+            // M = Rz(t) Rx(alpha) = [[c, -s ca, s sa], [s, c ca, -c sa], [0, sa, ca]]
+            const Real m01 = -s * ca, m02 = s * sa, m11 = c * ca, m12 = -c * sa;
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+                const Real r0 = R[3 * r], r1 = R[3 * r + 1], r2 = R[3 * r + 2];
+                R[3 * r] = r0 * c + r1 * s;
+                R[3 * r + 1] = r0 * m01 + r1 * m11 + r2 * sa;
+                R[3 * r + 2] = r0 * m02 + r1 * m12 + r2 * ca;
+            }
+        }
+    }
+    return ok;
+}
+
+struct FkArgs {
+    const void *angles;
+    int angles_f64;
+    long long n;
+    long long index_base;
+    void *pos_out;        // nullable, n x 3 (angles dtype)
+    const void *targets;  // nullable, n x 3 (xyz dtype)
+    int xyz_f64;
+    void *err_out;        // nullable, n (angles dtype)
+    IkbDeviceStats *stats;
+    IkbRobot rc;
+};
+
+template <typename Real>
+__global__ void __launch_bounds__(256) fk_kernel(const FkArgs a)
+{
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    double err_sum = 0.0;
+    unsigned err_cnt = 0;
+    bool alpha_ok = true;
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+        alpha_ok &= !(a.rc.alpha[j] < -6.283185307179586) & !(a.rc.alpha[j] > 6.283185307179586);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += stride) {
+        Real th[4];
+        if (a.angles_f64) {
+            const double2 *p = reinterpret_cast<const double2 *>(a.angles) + 2 * i;
+            const double2 u = __ldg(p), v = __ldg(p + 1);
+            th[0] = (Real)u.x; th[1] = (Real)u.y; th[2] = (Real)v.x; th[3] = (Real)v.y;
+        } else {
+            const float4 u = __ldg(reinterpret_cast<const float4 *>(a.angles) + i);
+            th[0] = (Real)u.x; th[1] = (Real)u.y; th[2] = (Real)u.z; th[3] = (Real)u.w;
+        }
+        Real px, py, pz;
+        const bool ok = fk_position<Real>(a.rc, th, px, py, pz) & alpha_ok;
+        if (!ok) {
+            px = py = pz = (Real)__int_as_float(0x7fc00000);
+            atomicMin(&a.stats->first_fk_angle_range, a.index_base + i);
+        }
+        if (a.pos_out) {
+            if (a.angles_f64) {
+                double *o = reinterpret_cast<double *>(a.pos_out) + 3 * i;
+                o[0] = px; o[1] = py; o[2] = pz;
+            } else {
+                float *o = reinterpret_cast<float *>(a.pos_out) + 3 * i;
+                o[0] = (float)px; o[1] = (float)py; o[2] = (float)pz;
+            }
+        }
+        if (a.targets) {
+            double tx, ty, tz;
+            ikb_load_xyz(a.targets, a.xyz_f64, i, tx, ty, tz);
+            const Real dx = px - (Real)tx, dy = py - (Real)ty, dz = pz - (Real)tz;
+            const Real err = sqrt(dx * dx + dy * dy + dz * dz);
+            if (a.err_out) {
+                if (a.angles_f64)
+                    reinterpret_cast<double *>(a.err_out)[i] = err;
+                else
+                    reinterpret_cast<float *>(a.err_out)[i] = (float)err;
+            }
+            if (isfinite(err)) {
+                err_sum += (double)err;
+                ++err_cnt;
+            }
+        }
+    }
+    if (a.targets) {
+        err_sum = ikb_warp_sum(err_sum);
+        err_cnt = ikb_warp_sum(err_cnt);
+        if ((threadIdx.x & 31) == 0 && err_cnt) {
+            atomicAdd(&a.stats->sum_fk_error, err_sum);
+            atomicAdd(&a.stats->n_fk_error, (unsigned long long)err_cnt);
+        }
+    }
+}
+
+// all four cumulative homogeneous matrices (forward.py:79-94), fp64, one thread per angle set
+__global__ void fk_chain_kernel(const double *angles, long long n, double *chain_out, int *status,
+                                const IkbRobot rc)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n)
+        return;
+    const double TWO_PI = 6.283185307179586;
+    double T[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+    int st = 0;
+    for (int j = 0; j < 4; ++j) {
+        const double t = angles[4 * i + j], al = rc.alpha[j];
+        if (t < -TWO_PI || t > TWO_PI || al < -TWO_PI || al > TWO_PI)
+            st = 1;
+        double s, c;
+        sincos(t, &s, &c);
+        const double ca = rc.cos_alpha[j], sa = rc.sin_alpha[j], aj = rc.a[j], ej = rc.eps[j];
+        // D = Rz(t) Tz(e) Tx(a) Rx(alpha)
+        const double D[16] = {c, -s * ca, s * sa, aj * c,
+                              s, c * ca, -c * sa, aj * s,
+                              0, sa, ca, ej,
+                              0, 0, 0, 1};
+        double N[16];
+        for (int r = 0; r < 4; ++r)
+            for (int q = 0; q < 4; ++q) {
+                double acc = 0;
+                for (int m = 0; m < 4; ++m)
+                    acc += T[4 * r + m] * D[4 * m + q];
+                N[4 * r + q] = acc;
+            }
+        for (int m = 0; m < 16; ++m) {
+            T[m] = N[m];
+            chain_out[64 * i + 16 * j + m] = N[m];
+        }
+    }
+    status[i] = st;
+}
+
+struct LimitsArgs {
+    const void *xyz;
+    int xyz_f64;
+    long long n;
+    long long index_base;
+    IkbDeviceStats *stats;
+    IkbRobot rc;
+};
+
+// K0: reference InverseKinematics.check_limits (inverse.py:26-35) as a min-index reduction.
+__global__ void __launch_bounds__(256) check_limits_kernel(const LimitsArgs a)
+{
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    long long first = IKB_I64_MAX;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += stride) {
+        double x, y, z;
+        ikb_load_xyz(a.xyz, a.xyz_f64, i, x, y, z);
+        if (ikb_out_of_limits(a.rc, x, y, z) && i < first)
+            first = i;  // grid-stride order is increasing per thread
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const long long other = __shfl_xor_sync(IKB_FULL_MASK, first, o);
+        first = other < first ? other : first;
+    }
+    if ((threadIdx.x & 31) == 0 && first != IKB_I64_MAX)
+        atomicMin(&a.stats->first_out_of_limits, a.index_base + first);
+}
+
+// Dependent-FMA-chain microbenchmark: 8 independent chains per thread keep the pipe full.
+template <typename Real>
+__global__ void __launch_bounds__(256) fma_peak_kernel(Real *sink, int iters, Real seed)
+{
+    Real v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+        v[j] = seed + (Real)(threadIdx.x + j);
+    const Real m = (Real)0.999, c = (Real)0.001;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                v[j] = fma(v[j], m, c);
+    }
+    Real s = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+        s += v[j];
+    if (s == (Real)-1)
+        sink[0] = s;
+}
+
+}  // namespace
+
+static unsigned ikb_stream_grid(long long n, int num_sms, int threads, int ctas_per_sm)
+{
+    long long want = (n + threads - 1) / threads;
+    long long cap = (long long)num_sms * ctas_per_sm;
+    return (unsigned)(want < cap ? (want > 0 ? want : 1) : cap);
+}
+
+cudaError_t ikb_launch_fk(const void *angles, int angles_f64, long long n, long long index_base,
+                          void *pos_out, const void *targets, int xyz_f64, void *err_out,
+                          IkbDeviceStats *stats, const IkbRobot &rc, int num_sms, cudaStream_t stream)
+{
+    if (n <= 0)
+        return cudaSuccess;
+    FkArgs a;
+    a.angles = angles; a.angles_f64 = angles_f64; a.n = n; a.index_base = index_base;
+    a.pos_out = pos_out; a.targets = targets; a.xyz_f64 = xyz_f64; a.err_out = err_out;
+    a.stats = stats; a.rc = rc;
+    const unsigned grid = ikb_stream_grid(n, num_sms, 256, 8);
+    if (angles_f64)
+        fk_kernel<double><<<grid, 256, 0, stream>>>(a);
+    else
+        fk_kernel<float><<<grid, 256, 0, stream>>>(a);
+    return cudaGetLastError();
+}
+
+cudaError_t ikb_launch_fk_chain(const double *angles, long long n, double *chain_out, int *status,
+                                const IkbRobot &rc, cudaStream_t stream)
+{
+    if (n <= 0)
+        return cudaSuccess;
+    fk_chain_kernel<<<(unsigned)((n + 63) / 64), 64, 0, stream>>>(angles, n, chain_out, status, rc);
+    return cudaGetLastError();
+}
+
+cudaError_t ikb_launch_check_limits(const void *xyz, int xyz_f64, long long n, long long index_base,
+                                    IkbDeviceStats *stats, const IkbRobot &rc, int num_sms,
+                                    cudaStream_t stream)
+{
+    if (n <= 0)
+        return cudaSuccess;
+    LimitsArgs a;
+    a.xyz = xyz; a.xyz_f64 = xyz_f64; a.n = n; a.index_base = index_base; a.stats = stats; a.rc = rc;
+    check_limits_kernel<<<ikb_stream_grid(n, num_sms, 256, 8), 256, 0, stream>>>(a);
+    return cudaGetLastError();
+}
+
+cudaError_t ikb_launch_fma_peak(int f64, void *sink, int iters, int num_sms, cudaStream_t stream)
+{
+    if (f64)
+        fma_peak_kernel<double><<<num_sms * 8, 256, 0, stream>>>((double *)sink, iters, 1.0);
+    else
+        fma_peak_kernel<float><<<num_sms * 8, 256, 0, stream>>>((float *)sink, iters, 1.0f);
+    return cudaGetLastError();
+}

@@ -1,0 +1,112 @@
+// ikb_common.cuh -- shared device-side definitions of libikb200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/ikb200.h"
+
+#define IKB_FULL_MASK 0xffffffffu
+#define IKB_I64_MAX 0x7fffffffffffffffLL
+
+// Robot / solver constants handed to every kernel by value (kernel parameter space, broadcast
+// through the constant bank).  Derived once on the host from ikb_config.
+struct IkbRobot {
+    // seed chain of FabrikInverseKinematics.ikine (reference inverse.py:123-130): FK of
+    // [theta_1, dh[0][1], dh[0][2], dh[0][3]].  Rz(theta_1) is the left-most factor of the DH
+    // product, so the chain is the theta_1 = 0 chain rotated about z by theta_1 = atan2(y, x);
+    // when that chain lies in the x-z plane (`planar`), chain and target share the vertical plane
+    // through the z axis and the whole solve is 2-D in (r, z).
+    double seed_r[4], seed_z[4];
+    double seed_xyz[12];  // the theta_1 = 0 chain in 3-D (generic path)
+    double links[4];      // joints_distances
+    double limits[6];     // xlo, xhi, ylo, yhi, zlo, zhi
+    double tol;
+    int max_iter;
+    int planar;
+    int zero_iter;        // tol >= 1 or max_iter <= 0: the reference's while loop never runs
+    // forward kinematics, reference forward.py:62-70: T_i = Rz(th_i) Tz(eps_i) Tx(a_i) Rx(alpha_i)
+    double eps[4], a[4], cos_alpha[4], sin_alpha[4], alpha[4];
+};
+
+// Device-side statistics block; host mirror is ikb_stats.  first_* start at IKB_I64_MAX.
+struct IkbDeviceStats {
+    unsigned long long n_solved;
+    unsigned long long sum_iterations;
+    unsigned long long n_iter_capped;
+    long long first_out_of_limits;
+    long long first_zero_division;
+    long long first_domain_error;
+    long long first_fk_angle_range;
+    double sum_fk_error;
+    unsigned long long n_fk_error;
+};
+
+__device__ __forceinline__ unsigned ikb_lanemask_lt()
+{
+    unsigned m;
+    asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+    return m;
+}
+
+// AoS target row i as doubles from an fp32 or fp64 buffer.
+__device__ __forceinline__ void ikb_load_xyz(const void *xyz, int f64, long long i, double &x,
+                                             double &y, double &z)
+{
+    if (f64) {
+        const double *p = reinterpret_cast<const double *>(xyz) + 3 * i;
+        x = __ldg(p); y = __ldg(p + 1); z = __ldg(p + 2);
+    } else {
+        const float *p = reinterpret_cast<const float *>(xyz) + 3 * i;
+        x = (double)__ldg(p); y = (double)__ldg(p + 1); z = (double)__ldg(p + 2);
+    }
+}
+
+// reference inverse.py:26-35: any axis < lo or > hi (NaN compares False and passes)
+__device__ __forceinline__ bool ikb_out_of_limits(const IkbRobot &rc, double x, double y, double z)
+{
+    return (x < rc.limits[0]) | (x > rc.limits[1]) | (y < rc.limits[2]) | (y > rc.limits[3]) |
+           (z < rc.limits[4]) | (z > rc.limits[5]);
+}
+
+__device__ __forceinline__ void ikb_store_angles(void *out, int f64, long long i, const double th[4])
+{
+    if (f64) {
+        double2 *p = reinterpret_cast<double2 *>(out) + 2 * i;
+        p[0] = make_double2(th[0], th[1]);
+        p[1] = make_double2(th[2], th[3]);
+    } else {
+        reinterpret_cast<float4 *>(out)[i] =
+            make_float4((float)th[0], (float)th[1], (float)th[2], (float)th[3]);
+    }
+}
+
+// 1/sqrt(x): one MUFU.RSQ64H seed (rsqrt.approx.ftz.f64, ~2^-22 relative) followed by one
+// third-order correction y(1 + e/2 + 3e^2/8), e = 1 - x y^2 -- 5 DP instructions, result good to
+// ~1 ulp for normal x.  x == 0 yields inf * 0 -> NaN downstream, which is how a zero-length segment
+// (ZeroDivisionError in reference point.py:40) is detected; no slow-path branches.
+__device__ __forceinline__ double ikb_rsqrt(double x)
+{
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    double t = y * y;
+    double e = fma(-x, t, 1.0);
+    double p = fma(e, 0.375, 0.5);
+    double q = y * e;
+    return fma(q, p, y);
+}
+
+__device__ __forceinline__ float ikb_rsqrt(float x)
+{
+    float y;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+template <typename T>
+__device__ __forceinline__ T ikb_warp_sum(T v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+        v += __shfl_xor_sync(IKB_FULL_MASK, v, o);
+    return v;
+}

@@ -1,0 +1,88 @@
+"""GPU parity of K2 (fused scaler -> MLP -> scaler).  Tolerance (BASELINE.json north_star): joint
+angles within 1e-5 rad of the fp32 (Keras-grade) computation.  ANN parity is UNPINNED against the
+real reference network (its weights are absent from the reference mount): the checker is the NumPy
+restatement of ann.py:70-76 with seeded synthetic weights of the ann.py:46-56 architecture."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+TOL_NORTH_STAR = 1e-5  # rad
+
+
+def _make(dims, seed):
+    from inversekinematicsann_b200.kinematics.inverse import AnnInverseKinematics
+    from inversekinematicsann_b200.robot.robot import SixDOFRobot as R
+    from oracle import np_oracle
+    W, b = np_oracle.synthetic_mlp(seed=seed, dims=dims)
+    ann = AnnInverseKinematics(R.dh_matrix, R.links_lengths, R.effector_workspace_limits)
+    ann.ann.set_model(W, b, np_oracle.SHIPPED_MEAN_X, np_oracle.SHIPPED_SCALE_X,
+                      np_oracle.SHIPPED_MEAN_Y, np_oracle.SHIPPED_SCALE_Y)
+    return ann, W, b
+
+
+def _points(n, seed=0):
+    rng = np.random.default_rng(seed)
+    return rng.uniform([0, -6, -3], [6, 6, 6], size=(n, 3))
+
+
+def test_full_architecture_vs_fp32_oracle():
+    from oracle import np_oracle
+    ann, W, b = _make(np_oracle.LAYER_DIMS, seed=1234)
+    xyz = _points(20_000)
+    got = ann.ikine(xyz, as_array=True)
+    want32 = np_oracle.mlp_predict(xyz, W, b)
+    want64 = np_oracle.mlp_predict(xyz, W, b, dtype=np.float64)
+    assert got.dtype == np.float32 and got.shape == (20_000, 4)
+    e32, e64 = np.abs(got - want32).max(), np.abs(got - want64).max()
+    print(f"max |dtheta| vs fp32 oracle {e32:.3e}, vs fp64 oracle {e64:.3e}, "
+          f"fp32 oracle vs fp64 oracle {np.abs(want32 - want64).max():.3e}")
+    assert e32 <= TOL_NORTH_STAR and e64 <= TOL_NORTH_STAR
+    as_list = ann.ikine(xyz[:3].tolist())
+    assert isinstance(as_list, list) and isinstance(as_list[0][0], float)
+
+
+@pytest.mark.parametrize("n", [1, 63, 64, 65, 1000])
+@pytest.mark.parametrize("dims", [[3, 64, 4], [3, 100, 50, 4], [3, 500, 500, 500, 4]])
+def test_ragged_sizes_and_small_nets(n, dims):
+    from oracle import np_oracle
+    ann, W, b = _make(dims, seed=7)
+    xyz = _points(n, seed=n)
+    got = ann.ann.predict(xyz)
+    want = np_oracle.mlp_predict(xyz, W, b)
+    assert np.abs(got - want).max() <= TOL_NORTH_STAR
+
+
+def test_limits_and_errors():
+    from inversekinematicsann_b200.kinematics.ann import ANN
+    from inversekinematicsann_b200.robot.robot import OutOfRobotReachException, SixDOFRobot as R
+    ann, W, b = _make([3, 64, 4], seed=2)
+    with pytest.raises(OutOfRobotReachException):      # reference tests/inverse_unit.py:59-62
+        ann.ikine([[1.0, 2.1, 3.0], [1.567, 2.22, -3.123], [1.02, 3.33, 4.99]])
+    out = ann.ann.predict([[-1.567, 2.22, -3.123]])    # predict has no limit check (ann_unit.py:39)
+    assert out.shape == (1, 4) and np.isfinite(out).all()
+    assert ann.ikine([]) == []
+    with pytest.raises(RuntimeError):
+        ANN(R.effector_workspace_limits, R.dh_matrix).predict([[1, 2, 3]])
+
+
+def test_model_files_round_trip(tmp_path):
+    """reference tests/ann_unit.py:23-35 (load_model / save_model), with the flat .npz container."""
+    import glob
+    from inversekinematicsann_b200.kinematics.ann import ANN
+    from inversekinematicsann_b200.robot.robot import SixDOFRobot as R
+    from sklearn.preprocessing import StandardScaler
+    from oracle import np_oracle
+    ann, W, b = _make([3, 64, 32, 4], seed=5)
+    sx, sy = StandardScaler().fit(_points(100)), StandardScaler().fit(np.random.default_rng(1).normal(size=(100, 4)))
+    ann.ann.x_data_skaler, ann.ann.y_data_skaler = sx, sy
+    ann.ann._uploaded = False
+    prefix = ann.ann.save_model(str(tmp_path / "saved_model"))
+    assert glob.glob(str(tmp_path / "saved_model*.npz"))
+    assert glob.glob(str(tmp_path / "saved_model*_scaler_x.bin")) and glob.glob(str(tmp_path / "saved_model*_scaler_y.bin"))
+    fresh = ANN(R.effector_workspace_limits, R.dh_matrix)
+    assert fresh.model is None
+    assert fresh.load_model(prefix + ".h5") is not None and fresh.model is not None
+    xyz = _points(200, seed=9)
+    want = np_oracle.mlp_predict(xyz, W, b, sx.mean_, sx.scale_, sy.mean_, sy.scale_)
+    assert np.abs(fresh.predict(xyz) - want).max() <= TOL_NORTH_STAR
