@@ -42,46 +42,105 @@ struct PlanarChain {
     Real r1, z1, r2, z2;  // joints 1 and 2; joint 0 is pinned, joint 3 is derived
 };
 
+// Convergence band of one end of the chain: |sqrt(n2) - d| > tol  <=>  n2 outside [lo2, hi2] with
+// lo2 = max(d - tol, 0)^2, hi2 = (d + tol)^2.  Testing the squared length saves the square root; the two
+// forms differ only when n2 sits within an ulp of a band edge (probability ~1e-13 per test in fp64).
+template <typename Real>
+struct Band {
+    Real lo2, hi2;
+    __device__ __forceinline__ Band(double d, double tol)
+    {
+        const double lo = d - tol > 0.0 ? d - tol : 0.0, hi = d + tol;
+        lo2 = (Real)(lo * lo);
+        hi2 = (Real)(hi * hi);
+        if (!(d - tol > 0.0))
+            lo2 = (Real)-1;  // any n2 >= 0 is above the lower edge
+    }
+    __device__ __forceinline__ bool outside(Real n2) const { return (n2 < lo2) | (n2 > hi2); }
+};
+
 // One forward-and-backward-reaching pass (reference fabrik.py:60-63) in the (r, z) plane.
 // Returns true when the reference's loop condition (start_error > tol or goal_error > tol) holds.
+// start_error = |b0 - S| = | |S - b1| - d0 | and goal_error = |f3 - T| = | |T - f2| - d3 |, because b0 and
+// f3 are the points at distance d0 / d3 from b1 / f2 towards S / T.
 template <typename Real>
 __device__ __forceinline__ bool fabrik_pass(PlanarChain<Real> &c, Real Tr, Real Tz, Real R0, Real Z0,
-                                            Real d0, Real d1, Real d2, Real d3, Real tol)
+                                            Real d1, Real d2, const Band<Real> &start_band,
+                                            const Band<Real> &goal_band)
 {
     // backward (fabrik.py:19-29): b3 = T, b2 = PB(b3, P2, d2), b1 = PB(b2, P1, d1), b0 = PB(b1, P0, d0)
     Real dr = c.r2 - Tr, dz = c.z2 - Tz;
     Real s = d2 * ikb_rsqrt(dr * dr + dz * dz);
-    Real b2r = Tr + s * dr, b2z = Tz + s * dz;
+    const Real b2r = Tr + s * dr, b2z = Tz + s * dz;
     dr = c.r1 - b2r; dz = c.z1 - b2z;
     s = d1 * ikb_rsqrt(dr * dr + dz * dz);
-    Real b1r = b2r + s * dr, b1z = b2z + s * dz;
+    const Real b1r = b2r + s * dr, b1z = b2z + s * dz;
     dr = R0 - b1r; dz = Z0 - b1z;
     Real n2 = dr * dr + dz * dz;
-    Real rs = ikb_rsqrt(n2);
-    Real se = fabs(n2 * rs - d0);  // |b0 - S| = | |S - b1| - d0 |            (fabrik.py:61)
+    const bool start_off = start_band.outside(n2);                       // fabrik.py:61
     // forward (fabrik.py:32-42): f0 = S, f1 = PB(f0, b1, d1), f2 = PB(f1, b2, d2), f3 = PB(f2, b3, d3)
-    s = d1 * rs;
+    s = d1 * ikb_rsqrt(n2);
     c.r1 = R0 - s * dr; c.z1 = Z0 - s * dz;  // (b1 - S) = -(dr, dz)
     dr = b2r - c.r1; dz = b2z - c.z1;
     s = d2 * ikb_rsqrt(dr * dr + dz * dz);
     c.r2 = c.r1 + s * dr; c.z2 = c.z1 + s * dz;
     dr = Tr - c.r2; dz = Tz - c.z2;
-    n2 = dr * dr + dz * dz;
-    Real ge = fabs(n2 * ikb_rsqrt(n2) - d3);  // |f3 - T| = | |T - f2| - d3 |   (fabrik.py:63)
-    return (se > tol) | (ge > tol);
+    n2 = dr * dr + dz * dz;                   // f3 itself is only needed after the last pass
+    return start_off | goal_band.outside(n2);                            // fabrik.py:63
+}
+
+#define IKB_FABRIK_IDLE_T 4  // lanes allowed to sit idle before the warp leaves its inner loop to refill
+
+// sqrt(x) for x >= 0 through the reciprocal square root (2 ulp); exact 0 for x == 0
+__device__ __forceinline__ double fast_sqrt(double x)
+{
+    const double s = x * ikb_rsqrt(x);
+    return x == 0.0 ? 0.0 : s;
+}
+
+// a / b: MUFU.RCP64H seed, two Newton steps, one residual correction (faithful to ~1 ulp)
+__device__ __forceinline__ double fast_div(double a, double b)
+{
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(b));
+    double e = fma(-b, y, 1.0);
+    y = fma(y, e, y);
+    e = fma(-b, y, 1.0);
+    y = fma(y, e, y);
+    const double q = a * y;
+    return fma(fma(-b, q, a), y, q);
 }
 
 __device__ __forceinline__ double dist2d(double ar, double az, double br, double bz)
 {
-    double dr = ar - br, dz = az - bz;
-    return sqrt(dr * dr + dz * dz);
+    const double dr = ar - br, dz = az - bz;
+    return fast_sqrt(dr * dr + dz * dz);
 }
 
-// round(x, 8) of reference inverse.py:81,92,100 (np.round-style rint(x * 1e8) / 1e8)
-__device__ __forceinline__ double round8(double x) { return rint(x * 1e8) / 1e8; }
+// round(x, 8) of reference inverse.py:81,92,100: q = rint(x * 1e8) is an integer, q / 1e8 is formed as
+// q * 1e-8 plus one exact-residual correction (1e8 is exactly representable), which reproduces the
+// correctly rounded quotient np.round / Python's round give, in particular exactly +-1.0 at q = +-1e8.
+__device__ __forceinline__ double round8(double x)
+{
+    const double q = rint(x * 1e8);
+    const double r = q * 1e-8;
+    return fma(fma(-r, 1e8, q), 1e-8, r);
+}
 
-// Finish one solved chain: derive the effector, lift to 3-D, extract the four angles in fp64
-// exactly as reference inverse.py:54-112 does, write outputs, raise the per-row flags.
+// In-plane radius of a target and the unit direction of its vertical plane.  Targets on the z axis
+// have no direction (the reference's theta_1 is rounding noise there): +x is used.
+__device__ __forceinline__ double planar_radius(double x, double y, double &ux, double &uy)
+{
+    const double n2 = x * x + y * y;
+    const double rs = ikb_rsqrt(n2);
+    const bool on_axis = (n2 == 0.0);
+    ux = on_axis ? 1.0 : x * rs;
+    uy = on_axis ? 0.0 : y * rs;
+    return on_axis ? 0.0 : n2 * rs;
+}
+
+// Finish one solved chain: derive the effector, lift to 3-D, extract the four angles in fp64 as
+// reference inverse.py:54-112 does, write outputs, raise the per-row flags.
 __device__ __forceinline__ void fabrik_epilogue(const FabrikArgs &a, int idx, int k, double r1,
                                                 double z1, double r2, double z2)
 {
@@ -92,7 +151,8 @@ __device__ __forceinline__ void fabrik_epilogue(const FabrikArgs &a, int idx, in
     const long long row = a.index_base + idx;
     if (ikb_out_of_limits(rc, x, y, z))
         atomicMin(&a.stats->first_out_of_limits, row);
-    const double Tr = sqrt(x * x + y * y), Tz = z;
+    double ux, uy;
+    const double Tr = planar_radius(x, y, ux, uy), Tz = z;
     const double R0 = rc.seed_r[0], Z0 = rc.seed_z[0];
     double r3, z3;
     bool zero_div = false;
@@ -100,42 +160,40 @@ __device__ __forceinline__ void fabrik_epilogue(const FabrikArgs &a, int idx, in
         r1 = rc.seed_r[1]; z1 = rc.seed_z[1]; r2 = rc.seed_r[2]; z2 = rc.seed_z[2];
         r3 = rc.seed_r[3]; z3 = rc.seed_z[3];
     } else {       // f3 = PB(f2, T, d3) (fabrik.py:40)
-        double dr = Tr - r2, dz = Tz - z2;
-        double n = sqrt(dr * dr + dz * dz);
-        zero_div |= (n == 0.0);
-        double s = rc.links[3] / n;
+        const double dr = Tr - r2, dz = Tz - z2;
+        const double n2 = dr * dr + dz * dz;
+        zero_div |= (n2 == 0.0);
+        const double s = rc.links[3] * ikb_rsqrt(n2);
         r3 = r2 + s * dr; z3 = z2 + s * dz;
     }
     // a NaN chain from finite input can only come from 0 * inf, i.e. a zero-length segment
     const bool finite_in = isfinite(x) & isfinite(y) & isfinite(z);
     zero_div |= finite_in & !(isfinite(r1) & isfinite(z1) & isfinite(r2) & isfinite(z2));
-    // horizontal direction of the solve plane; targets on the z axis have no direction (the
-    // reference's theta_1 is rounding noise there): use +x.
-    const double ux = Tr > 0.0 ? x / Tr : 1.0, uy = Tr > 0.0 ? y / Tr : 0.0;
     double th[4];
     th[0] = atan2(r3 * uy, r3 * ux);                                    // inverse.py:60
-    const double ab = sqrt(R0 * R0 + Z0 * Z0);                           // A = origin
+    const double ab = fast_sqrt(R0 * R0 + Z0 * Z0);                      // A = origin
     const double bc = dist2d(R0, Z0, r1, z1), cd = dist2d(r1, z1, r2, z2);
     const double de = dist2d(r2, z2, r3, z3);
-    const double ac = sqrt(r1 * r1 + z1 * z1);
+    const double ac = fast_sqrt(r1 * r1 + z1 * z1);
     const double bd = dist2d(R0, Z0, r2, z2), ce = dist2d(r1, z1, r3, z3);
     double den = 2 * ab * bc;
     zero_div |= (den == 0.0);
-    const double c2 = round8((ab * ab + bc * bc - ac * ac) / den);       // inverse.py:77-81
+    const double c2 = round8(fast_div(ab * ab + bc * bc - ac * ac, den));   // inverse.py:77-81
     const double acos2 = acos(c2);
     th[1] = ((r1 * ux) * (r2 * ux) < 0) ? (3 * PI / 2) - acos2 : -(PI / 2 - acos2);  // :82-85
     den = 2 * bc * cd;
     zero_div |= (den == 0.0);
-    const double c3 = round8((bc * bc + cd * cd - bd * bd) / den);       // :90-92
+    const double c3 = round8(fast_div(bc * bc + cd * cd - bd * bd, den));   // :90-92
     th[2] = -(PI - acos(c3));                                            // :93
     den = 2 * cd * de;
     zero_div |= (den == 0.0) | (ce == 0.0);
-    const double c4 = round8((cd * cd + de * de - ce * ce) / den);       // :98-100
+    const double c4 = round8(fast_div(cd * cd + de * de - ce * ce, den));   // :98-100
     const double acos4 = acos(c4);
     // t4_point_bt = PB(C, E, |CE| / 2) (inverse.py:102): (|CE|/2)/|CE| is exactly 0.5
     const double mr = r1 + 0.5 * (r3 - r1), mz = z1 + 0.5 * (z3 - z1);
     const double dista = dist2d(R0, Z0, mr, mz);
     th[3] = (bd > dista) ? -(PI - acos4) : (PI - acos4);                 // :103-108
+    zero_div &= finite_in;
     const bool domain = !zero_div & (fabs(c2) > 1.0 | fabs(c3) > 1.0 | fabs(c4) > 1.0);
     if (zero_div) {
         th[0] = th[1] = th[2] = th[3] = __longlong_as_double(0x7ff8000000000000LL);
@@ -163,11 +221,13 @@ __global__ void __launch_bounds__(IKB_FABRIK_WARPS * 32, 3) fabrik_planar_kernel
     const unsigned lt = ikb_lanemask_lt();
     const IkbRobot &rc = a.rc;
     const Real R0 = (Real)rc.seed_r[0], Z0 = (Real)rc.seed_z[0];
-    const Real d0 = (Real)rc.links[0], d1 = (Real)rc.links[1], d2 = (Real)rc.links[2],
-               d3 = (Real)rc.links[3], tol = (Real)rc.tol;
+    const Real d1 = (Real)rc.links[1], d2 = (Real)rc.links[2];
+    const Band<Real> start_band(rc.links[0], rc.tol), goal_band(rc.links[3], rc.tol);
     const int max_iter = rc.max_iter;
+    const bool zero_iter = rc.zero_iter != 0;
 
     bool active = false, exhausted = false;
+    unsigned active_mask = 0;  // warp-uniform copy of `active`
     int idx = 0, k = 0;
     Real Tr = 0, Tz = 0;
     PlanarChain<Real> c{0, 0, 0, 0};
@@ -177,7 +237,7 @@ __global__ void __launch_bounds__(IKB_FABRIK_WARPS * 32, 3) fabrik_planar_kernel
     unsigned solved_local = 0, capped_local = 0;
 
     for (;;) {
-        // 1. top up the input queue, one coalesced full-warp load of up to 32 targets
+        // 1. top up the input queue: one coalesced full-warp load of up to 32 targets
         if (in_cnt <= 32 && !exhausted) {
             if (cur == cur_end) {
                 unsigned long long base = 0;
@@ -194,11 +254,11 @@ __global__ void __launch_bounds__(IKB_FABRIK_WARPS * 32, 3) fabrik_planar_kernel
             if (!exhausted) {
                 const int m = (int)min((long long)32, cur_end - cur);
                 if (lane < m) {
-                    double x, y, z;
+                    double x, y, z, ux, uy;
                     ikb_load_xyz(a.xyz, a.xyz_f64, cur + lane, x, y, z);
                     const int slot = (in_head + in_cnt + lane) & (IKB_Q - 1);
                     s_in_idx[w][slot] = (int)(cur + lane);
-                    s_in_tr[w][slot] = (Real)sqrt(x * x + y * y);
+                    s_in_tr[w][slot] = (Real)planar_radius(x, y, ux, uy);
                     s_in_tz[w][slot] = (Real)z;
                 }
                 in_cnt += m;
@@ -207,8 +267,8 @@ __global__ void __launch_bounds__(IKB_FABRIK_WARPS * 32, 3) fabrik_planar_kernel
             }
         }
         // 2. idle lanes take the next staged targets
-        const unsigned need = __ballot_sync(IKB_FULL_MASK, !active);
-        if (need != 0 && in_cnt > 0) {
+        if (active_mask != IKB_FULL_MASK && in_cnt > 0) {
+            const unsigned need = ~active_mask;
             const int rank = __popc(need & lt);
             if (!active && rank < in_cnt) {
                 const int slot = (in_head + rank) & (IKB_Q - 1);
@@ -223,58 +283,61 @@ __global__ void __launch_bounds__(IKB_FABRIK_WARPS * 32, 3) fabrik_planar_kernel
             const int take = min(__popc(need), in_cnt);
             in_head = (in_head + take) & (IKB_Q - 1);
             in_cnt -= take;
+            active_mask = __ballot_sync(IKB_FULL_MASK, active);
+        }
+        // 3. FABRIK passes (reference fabrik.py:57-65).  Every lane executes the pass -- lanes without a
+        //    live chain compute on stale registers and are ignored -- so the loop body is branch-free;
+        //    a lane that finishes parks its chain at once and the warp only leaves the loop when
+        //    enough lanes idle to make a refill worthwhile or a full warp of parked chains is ready.
+        if (active_mask != 0) {
+            const int idle_limit = (exhausted && in_cnt == 0) ? 33 : IKB_FABRIK_IDLE_T;
+            int n_idle = 32 - __popc(active_mask);
+            do {
+                bool more = false;
+                if (!zero_iter) {
+                    more = fabrik_pass(c, Tr, Tz, R0, Z0, d1, d2, start_band, goal_band);
+                    ++k;
+                }
+                const bool fin = active & (!more | (k >= max_iter));
+                const unsigned m = __ballot_sync(IKB_FULL_MASK, fin);
+                if (m != 0) {
+                    if (fin) {
+                        const int slot = (out_head + out_cnt + __popc(m & lt)) & (IKB_Q - 1);
+                        s_out_idx[w][slot] = idx;
+                        s_out_k[w][slot] = k;
+                        s_out_c[w][0][slot] = c.r1; s_out_c[w][1][slot] = c.z1;
+                        s_out_c[w][2][slot] = c.r2; s_out_c[w][3][slot] = c.z2;
+                        iters_local += (unsigned)k;
+                        ++solved_local;
+                        capped_local += (more ? 1u : 0u);
+                        active = false;
+                    }
+                    const int nf = __popc(m);
+                    out_cnt += nf;
+                    n_idle += nf;
+                    active_mask &= ~m;
+                }
+            } while (n_idle < idle_limit && out_cnt < 32 && active_mask != 0);
             __syncwarp();
         }
-        if (__ballot_sync(IKB_FULL_MASK, active) == 0) {
-            if (exhausted && in_cnt == 0)
-                break;
-            continue;
-        }
-        // 3. one FABRIK pass for every active lane (reference fabrik.py:57-65)
-        bool done = false;
-        if (active) {
-            if (rc.zero_iter) {
-                done = true;
-            } else {
-                const bool more = fabrik_pass(c, Tr, Tz, R0, Z0, d0, d1, d2, d3, tol);
-                ++k;
-                done = !more | (k >= max_iter);
-                if (done)
-                    capped_local += (more ? 1u : 0u);
-            }
-        }
-        // 4. park finished chains; run the epilogue once a full warp of them is waiting
-        const unsigned fin = __ballot_sync(IKB_FULL_MASK, done);
-        if (fin != 0) {
-            if (done) {
-                const int slot = (out_head + out_cnt + __popc(fin & lt)) & (IKB_Q - 1);
-                s_out_idx[w][slot] = idx;
-                s_out_k[w][slot] = k;
-                s_out_c[w][0][slot] = c.r1; s_out_c[w][1][slot] = c.z1;
-                s_out_c[w][2][slot] = c.r2; s_out_c[w][3][slot] = c.z2;
-                iters_local += (unsigned)k;
-                ++solved_local;
-                active = false;
-            }
-            out_cnt += __popc(fin);
-            __syncwarp();
-            if (out_cnt >= 32) {
+        // 4. the fp64 epilogue runs on a full warp of parked chains (or on the remainder once all
+        //    work is done).  ONE call site: every row goes through the same instruction sequence,
+        //    so results do not depend on where in the batch a target sits.
+        const bool drained = active_mask == 0 && exhausted && in_cnt == 0;
+        if (out_cnt >= 32 || (drained && out_cnt > 0)) {
+            const int n_take = min(32, out_cnt);
+            if (lane < n_take) {
                 const int slot = (out_head + lane) & (IKB_Q - 1);
                 fabrik_epilogue(a, s_out_idx[w][slot], s_out_k[w][slot], (double)s_out_c[w][0][slot],
                                 (double)s_out_c[w][1][slot], (double)s_out_c[w][2][slot],
                                 (double)s_out_c[w][3][slot]);
-                out_head = (out_head + 32) & (IKB_Q - 1);
-                out_cnt -= 32;
-                __syncwarp();
             }
+            out_head = (out_head + n_take) & (IKB_Q - 1);
+            out_cnt -= n_take;
+            __syncwarp();
         }
-    }
-    // drain the parked chains that never filled a whole warp
-    if (lane < out_cnt) {
-        const int slot = (out_head + lane) & (IKB_Q - 1);
-        fabrik_epilogue(a, s_out_idx[w][slot], s_out_k[w][slot], (double)s_out_c[w][0][slot],
-                        (double)s_out_c[w][1][slot], (double)s_out_c[w][2][slot],
-                        (double)s_out_c[w][3][slot]);
+        if (drained && out_cnt == 0)
+            break;
     }
     // statistics: one atomic per warp and counter
     const unsigned long long it = ikb_warp_sum(iters_local);

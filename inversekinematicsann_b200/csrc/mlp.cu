@@ -22,7 +22,7 @@ constexpr int THREADS = 256;
 constexpr int MAXW = IKB_MLP_MAX_WIDTH;
 constexpr size_t SMEM_A = (size_t)MAXW * TM * sizeof(float);          // 128 KB activations
 constexpr size_t SMEM_W = (size_t)2 * KC * MAXW * sizeof(float);      // 64 KB weight ring
-constexpr size_t SMEM_MISC = 1024;                                    // barriers + output staging
+constexpr size_t SMEM_MISC = 2048;                                    // barriers + output staging
 constexpr size_t SMEM_TOTAL = SMEM_A + SMEM_W + SMEM_MISC;
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p)

@@ -82,12 +82,18 @@ class FabrikInverseKinematics(InverseKinematics):
         self.precision = precision
         self.last_stats = None
 
-    def ikine(self, dest_points, as_array=False, return_iterations=False):
-        """Joint angles [theta1..theta4] for every destination point."""
+    def ikine(self, dest_points, as_array=False, return_iterations=False, out=None):
+        """Joint angles [theta1..theta4] for every destination point.
+
+        `out` (optional, implies as_array): a preallocated (n, 4) float32/float64 array -- e.g. pinned
+        host memory -- that receives the angles."""
         arr = points_to_array(dest_points)
         if arr.shape[0] == 0:
             return np.zeros((0, 4)) if as_array else []
-        res = self._engine().fabrik_solve(arr, precision=self.precision, return_iters=return_iterations)
+        if out is not None:
+            as_array = True
+        res = self._engine().fabrik_solve(arr, out=out, precision=self.precision,
+                                          return_iters=return_iterations)
         angles, stats = res[0], res[1]
         self.last_stats = stats
         self._raise_from_stats(dest_points, stats)
@@ -107,12 +113,14 @@ class AnnInverseKinematics(InverseKinematics):
         """Load model weights + scalers (reference inverse.py:148-150)."""
         self.ann.load_model(model_name)
 
-    def ikine(self, dest_points, as_array=False):
+    def ikine(self, dest_points, as_array=False, out=None):
         """Predict thetas using the neural network (limits checked first, inverse.py:154)."""
         arr = points_to_array(dest_points)
         if arr.shape[0] == 0:
             return np.zeros((0, 4), dtype=np.float32) if as_array else []
-        angles, stats = self.ann.predict_with_stats(arr)
+        if out is not None:
+            as_array = True
+        angles, stats = self.ann.predict_with_stats(arr, out=out)
         self.last_stats = stats
         self._raise_from_stats(dest_points, stats)
         return angles if as_array else angles.tolist()

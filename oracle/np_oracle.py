@@ -27,7 +27,7 @@ SHIPPED_SCALE_Y = np.array([0.8768847052996848, 0.6520665510519178, 1.0214536342
 LAYER_DIMS = [3] + [500] * 12 + [4]  # ann.py:46-56: Input(3), 12 x Dense(500, tanh), Dense(4)
 
 
-def synthetic_mlp(seed=1234, dims=LAYER_DIMS, gain=1.5, bias_range=0.1):
+def synthetic_mlp(seed=1234, dims=LAYER_DIMS, gain=1.0, bias_range=0.1):
     """Seeded Glorot-uniform kernels (Keras' default initialiser, scaled by `gain` so the tanh units
     are neither dead nor saturated) and small uniform biases.  Returns (weights, biases) float32."""
     rng = np.random.default_rng(seed)
