@@ -1,0 +1,390 @@
+#!/usr/bin/env python
+"""Headline benchmark: batched IK solves/s of the B200 engine (FABRIK + ANN) beside the CPU restatement.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+Under torchrun (N > 1) every rank solves its own contiguous shard of the trajectory (weak scaling:
+`--rows` FABRIK targets per GPU); rank 0 prints ONE JSON line.  A "step" is one pass of the hot path
+(check_limits + FABRIK + fp64 angle extraction) over the rank's batch of synthetic cube_random targets,
+inputs resident in HBM (`value`), or host-resident and pushed through the public
+FabrikInverseKinematics.ikine() call (`e2e`).  The ANN path (config 2) rides in the same line under "ann".
+
+`--impl reference` times the CPU restatement of the reference's algorithm (oracle/ik_oracle.c, all host
+threads; the reference itself is pure Python and cannot travel to the GPU box) on bounded samples of the
+same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "IK solves/sec (FABRIK, cube_random full workspace, tol 1e-3 / 100 iterations)"
+UNIT = "solves/s"
+WORKSPACE_BOX = ((6.0, 12.0, 9.0), (0.0, -6.0, -3.0))   # SURVEY 8d cfg 3 (W): len, start
+INTERIOR_BOX = ((2.0, 4.0, 3.0), (1.0, -2.0, 1.0))      # SURVEY 8d cfg 3 (R)
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--rows", type=int, default=100_000_000, help="FABRIK targets per GPU (config 3)")
+    ap.add_argument("--ann-rows", type=int, default=1_000_000, help="ANN targets per GPU (config 2)")
+    ap.add_argument("--e2e-rows", type=int, default=0, help="host-resident rows per GPU for e2e (0 = --rows)")
+    ap.add_argument("--skip-ann", action="store_true")
+    ap.add_argument("--skip-cpu", action="store_true")
+    return ap.parse_args()
+
+
+# ---- clocks -----------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons of one GPU while the timed region runs."""
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.samples, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}",
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+
+    def summary(self, t0, t1):
+        rows = [r for t, r in self.samples if t0 <= t <= t1] or [r for _, r in self.samples[-3:]]
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        sm = sorted(float(r[0]) for r in rows if r[0].replace(".", "").isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 3 + i and r[3 + i] == "Active" for r in rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(rows[0][1]),
+                "power_w_max": max(float(r[2]) for r in rows), "samples": len(rows), "reasons": reasons}
+
+
+# ---- CPU arm (oracle port) -----------------------------------------------------------------------------
+def host_points(n, box, seed):
+    rng = np.random.RandomState(seed)
+    ln, st = box
+    return rng.rand(n, 3) * np.array(ln) + np.array(st)
+
+
+def cpu_fabrik_rate(sample_rows, box, seed=1234, repeats=1):
+    """solves/s of the C restatement (OpenMP, all host threads) on `sample_rows` targets."""
+    from oracle import c_oracle
+    pts = host_points(sample_rows, box, seed)
+    c_oracle.fabrik_ikine(pts[:1000])
+    best = float("inf")
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        res = c_oracle.fabrik_ikine(pts)
+        best = min(best, time.perf_counter() - t0)
+    return sample_rows / best, c_oracle.num_threads(), float(res["iters"].mean())
+
+
+def cpu_ann_rate(sample_rows, weights, biases, seed=1234):
+    """solves/s of the NumPy fp32 restatement (BLAS threads = all host cores)."""
+    from oracle import np_oracle
+    pts = host_points(sample_rows, WORKSPACE_BOX, seed)
+    np_oracle.mlp_predict(pts[:2048], weights, biases)
+    t0 = time.perf_counter()
+    np_oracle.mlp_predict(pts, weights, biases)
+    return sample_rows / (time.perf_counter() - t0)
+
+
+def calibrated_cpu_sample(box, target_seconds=12.0):
+    rate, threads, _ = cpu_fabrik_rate(200_000, box, repeats=2)
+    return int(max(100_000, min(20_000_000, rate * target_seconds))), threads
+
+
+def run_reference_arm(args, rank):
+    """The reference's own algorithm on the host cores: rank 0 only, bounded samples per step."""
+    if rank != 0:
+        return
+    from oracle import c_oracle
+    sample, threads = calibrated_cpu_sample(WORKSPACE_BOX, target_seconds=6.0)
+    pts = host_points(sample, WORKSPACE_BOX, 1234)
+    for _ in range(max(1, min(args.warmup, 2))):
+        c_oracle.fabrik_ikine(pts[: sample // 4])
+    t0 = time.perf_counter()
+    iters = 0.0
+    for _ in range(args.steps):
+        iters = float(c_oracle.fabrik_ikine(pts)["iters"].mean())
+    dt = time.perf_counter() - t0
+    value = sample * args.steps / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic", "gpu_launches": 0,
+        "config": {"workload": "fabrik cube_random full workspace box (0,-6,-3)+(6,12,9), seed 1234",
+                   "rows_per_step": sample, "mean_iterations": iters},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": f"{sample} targets per step x {args.steps} steps, oracle/ik_oracle.c "
+                                   f"(C restatement of fabrik.py + inverse.py, OpenMP); the reference is "
+                                   f"pure Python (~4e2 solves/s/core on this workload, BASELINE.md) and is "
+                                   f"not present on the GPU box"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---- GPU arm -----------------------------------------------------------------------------------------
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", 0))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    if args.impl == "reference":
+        run_reference_arm(args, rank)
+        return
+    if args.warmup < 3:
+        args.warmup = 3  # timing rule: at least 3 warm-up steps
+
+    import torch
+    import torch.distributed as dist
+    from inversekinematicsann_b200.engine import fabrik_algorithmic_flops
+    from inversekinematicsann_b200.kinematics.inverse import AnnInverseKinematics, FabrikInverseKinematics
+    from inversekinematicsann_b200.robot.robot import SixDOFRobot as R
+    from inversekinematicsann_b200.sharding import reduce_stats
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(seconds):
+        if world == 1:
+            return seconds
+        t = torch.tensor([seconds], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    ik = FabrikInverseKinematics(R.dh_matrix, R.links_lengths, R.effector_workspace_limits, device=local_rank)
+    eng = ik._engine()
+    n = args.rows
+
+    def device_points(rows, box, seed):
+        g = torch.Generator(device=dev).manual_seed(seed)
+        u = torch.rand(rows, 3, device=dev, generator=g, dtype=torch.float32)
+        ln, st = box
+        return u.mul_(torch.tensor(ln, device=dev)).add_(torch.tensor(st, device=dev))
+
+    def timed_device_loop(fn, steps, warmup):
+        """K steps bracketed by barrier + synchronize, CUDA events on torch's current stream (the stream
+        the kernels are launched on); returns (max-over-ranks seconds, wall t0, wall t1)."""
+        for _ in range(warmup):
+            fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        w0 = time.perf_counter()
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        w1 = time.perf_counter()
+        return max_over_ranks(e0.elapsed_time(e1) * 1e-3), w0, w1
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+
+    # ---- FABRIK, device resident (value + roofline) ----------------------------------------------
+    xyz = device_points(n, WORKSPACE_BOX, 1234 + rank)          # 1.2 GB >> 126 MB L2
+    angles = torch.empty(n, 4, device=dev, dtype=torch.float32)
+    eng.stats_reset_torch()
+    eng.fabrik_solve_device(xyz, angles)
+    one = eng.stats_fetch_torch()                               # per-launch iteration count (deterministic)
+    launches0 = eng.launch_count
+    secs, w0, w1 = timed_device_loop(lambda: eng.fabrik_solve_device(xyz, angles), args.steps, args.warmup)
+    gpu_launches = (eng.launch_count - launches0 - args.warmup) * world
+    value = n * world * args.steps / secs
+    total = reduce_stats(one)
+    flops_per_launch = fabrik_algorithmic_flops(one.sum_iterations, n)
+    launch_s = secs / args.steps
+    peak_fp64 = eng.microbench_fma("f64")
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    hbm_peak = json.load(open(peaks_path))["hbm_gbs"] if os.path.exists(peaks_path) else 6650.0
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "k1_traffic.json")
+    if os.path.exists(tpath):
+        t = json.load(open(tpath))
+        if t.get("rows") == n:
+            traffic = t.get("dram_bytes_per_launch")
+    roofline = {
+        "kernel": "fabrik_planar_kernel<double>", "bound": "fp64",
+        "achieved": flops_per_launch / launch_s / 1e12, "peak": peak_fp64, "unit": "TFLOP/s",
+        "frac": flops_per_launch / launch_s / 1e12 / peak_fp64,
+        "peak_source": "measured live: DFMA-chain microbenchmark (ikb_microbench_fma); MEASURED_PEAKS.json has no "
+                       "CUDA-core figure",
+        "flops_per_launch": flops_per_launch, "flops_model": "114*sum_iterations + 126*rows (SURVEY 8d)",
+        "launch_ms": launch_s * 1e3,
+        "hbm": {"achieved": n * 28 / launch_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                "frac": n * 28 / launch_s / 1e9 / hbm_peak,
+                "peak_source": "MEASURED_PEAKS.json" if os.path.exists(peaks_path) else "fallback"},
+        "traffic": traffic,
+    }
+
+    # FK position error of the solved angles (K3), once, outside the timed loop
+    err = torch.empty(n, device=dev, dtype=torch.float32)
+    eng.stats_reset_torch()
+    fk_secs, _, _ = timed_device_loop(lambda: eng.fk_device(angles, targets=xyz, err=err), 3, 1)
+    eng.stats_reset_torch()
+    eng.fk_device(angles, targets=xyz, err=err)
+    fk_stats = reduce_stats(eng.stats_fetch_torch())
+    reach = (xyz - torch.tensor([0.0, 0.0, 2.0], device=dev)).norm(dim=1) <= 6.0
+    fk_error = {"mean_all": fk_stats.mean_fk_error,
+                "median_reachable": float(err[reach][:20_000_000].median().item()),
+                "reachable_fraction": float(reach.float().mean().item()),
+                "fk_rows_per_s": n * world * 3 / fk_secs,
+                "fk_hbm_frac": n * 32 * 3 / fk_secs / 1e9 / hbm_peak}
+
+    # interior (fully reachable) box, secondary figure
+    xyz_r = device_points(min(n, 50_000_000), INTERIOR_BOX, 99 + rank)
+    ang_r = torch.empty(xyz_r.shape[0], 4, device=dev, dtype=torch.float32)
+    eng.stats_reset_torch()
+    eng.fabrik_solve_device(xyz_r, ang_r)
+    one_r = eng.stats_fetch_torch()
+    secs_r, _, _ = timed_device_loop(lambda: eng.fabrik_solve_device(xyz_r, ang_r), args.steps, 3)
+    interior = {"value": xyz_r.shape[0] * world * args.steps / secs_r, "unit": UNIT,
+                "rows_per_gpu": xyz_r.shape[0], "mean_iterations": one_r.sum_iterations / xyz_r.shape[0],
+                "fp64_frac": fabrik_algorithmic_flops(one_r.sum_iterations, xyz_r.shape[0]) /
+                             (secs_r / args.steps) / 1e12 / peak_fp64}
+    del xyz_r, ang_r, err
+
+    # ---- FABRIK end to end: host buffers through the public ikine() call --------------------------
+    m = args.e2e_rows or n
+    host_in = torch.empty(m, 3, dtype=torch.float32, pin_memory=True)
+    host_in.copy_(xyz[:m])
+    host_out = torch.empty(m, 4, dtype=torch.float32, pin_memory=True)
+    h_in, h_out = host_in.numpy(), host_out.numpy()
+    del xyz, angles
+    e2e_steps = max(2, min(args.steps, 5))
+    for _ in range(2):
+        ik.ikine(h_in, out=h_out)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        ik.ikine(h_in, out=h_out)          # H2D + solve + D2H, synchronous at the API boundary
+    torch.cuda.synchronize()
+    e2e_secs = max_over_ranks(time.perf_counter() - t0)
+    e2e = {"value": m * world * e2e_steps / e2e_secs, "unit": UNIT,
+           "h2d_bytes_per_step": m * 12 * world, "d2h_bytes_per_step": m * 16 * world,
+           "rows_per_gpu": m, "steps": e2e_steps,
+           "api": "FabrikInverseKinematics.ikine(float32 ndarray, out=pinned float32 ndarray)"}
+    del host_in, host_out
+
+    # ---- ANN (config 2) -------------------------------------------------------------------------------
+    ann_block = None
+    if not args.skip_ann:
+        from oracle import np_oracle  # synthetic weights only (the shipped .h5 is absent from the mount)
+        W, b = np_oracle.synthetic_mlp()
+        ann = AnnInverseKinematics(R.dh_matrix, R.links_lengths, R.effector_workspace_limits, device=local_rank)
+        ann.ann.set_model(W, b, np_oracle.SHIPPED_MEAN_X, np_oracle.SHIPPED_SCALE_X,
+                          np_oracle.SHIPPED_MEAN_Y, np_oracle.SHIPPED_SCALE_Y)
+        aeng = ann.ann._ensure_uploaded()
+        an = args.ann_rows
+        axyz = device_points(an, WORKSPACE_BOX, 4321 + rank)
+        aout = torch.empty(an, 4, device=dev, dtype=torch.float32)
+        a_steps = max(2, min(args.steps, 5))
+        a_launch0 = aeng.launch_count
+        a_secs, _, _ = timed_device_loop(lambda: aeng.ann_solve_device(axyz, aout), a_steps, 3)
+        gpu_launches += (aeng.launch_count - a_launch0 - 3) * world
+        a_in = torch.empty(an, 3, dtype=torch.float32, pin_memory=True)
+        a_in.copy_(axyz)
+        a_res = torch.empty(an, 4, dtype=torch.float32, pin_memory=True)
+        ann.ikine(a_in.numpy(), out=a_res.numpy())
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(a_steps):
+            ann.ikine(a_in.numpy(), out=a_res.numpy())
+        ae2e = max_over_ranks(time.perf_counter() - t0)
+        flops = 2.0 * aeng.mlp_macs_per_row * an
+        peak_fp32 = aeng.microbench_fma("f32")
+        ann_block = {
+            "metric": "IK solves/sec (ANN 3->12x500 tanh->4, fused scaler+MLP+scaler)", "value": an * world * a_steps / a_secs,
+            "unit": UNIT, "rows_per_gpu": an, "ms_per_step": a_secs / a_steps * 1e3, "dtype": "f32",
+            "mode": "fp32 FFMA on CUDA cores (IKB_MLP_FP32_SIMT)",
+            "weights": "synthetic seeded Glorot (shipped roboarm_model .h5 is missing from the reference mount; parity unpinned)",
+            "e2e": {"value": an * world * a_steps / ae2e, "unit": UNIT, "h2d_bytes_per_step": an * 12 * world,
+                    "d2h_bytes_per_step": an * 16 * world},
+            "roofline": {"kernel": "mlp_simt_kernel", "bound": "fp32", "achieved": flops / (a_secs / a_steps) / 1e12,
+                         "peak": peak_fp32, "unit": "TFLOP/s", "frac": flops / (a_secs / a_steps) / 1e12 / peak_fp32,
+                         "peak_source": "measured live: FFMA-chain microbenchmark", "flops_per_row": 2 * aeng.mlp_macs_per_row,
+                         "traffic": None},
+        }
+        if rank == 0 and not args.skip_cpu:
+            rows = 100_000
+            ann_block["cpu_baseline"] = {"value": cpu_ann_rate(rows, W, b), "unit": UNIT, "cores": os.cpu_count(),
+                                         "kind": "port", "sample": f"{rows} targets, NumPy fp32 restatement of ann.py:70-76 "
+                                                                   f"(BLAS threads = host cores); Keras is not installed"}
+
+    clocks = None
+    if rank == 0:
+        sampler.stop()
+        clocks = sampler.summary(w0, w1)
+
+    cpu_baseline = None
+    if rank == 0 and not args.skip_cpu:
+        sample, threads = calibrated_cpu_sample(WORKSPACE_BOX)
+        rate, threads, mean_it = cpu_fabrik_rate(sample, WORKSPACE_BOX)
+        cpu_baseline = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
+                        "sample": f"{sample} cube_random full-workspace targets (mean {mean_it:.1f} iterations), "
+                                  f"oracle/ik_oracle.c = C restatement of fabrik.py/inverse.py with OpenMP on all host "
+                                  f"threads; the pure-Python reference runs ~4e2 solves/s/core on this workload "
+                                  f"(BASELINE.md) and does not exist on the GPU box"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": secs / args.steps * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "BASELINE configs[2]: FABRIK on 100M cube_random targets per GPU, full workspace box "
+                                   "(0,-6,-3)+(6,12,9), torch Philox seed 1234+rank; configs[1] (ANN with the shipped .h5) "
+                                   "cannot run as stated because the weights are absent -- see \"ann\"",
+                       "rows_per_gpu": n, "input": "float32 [n,3] AoS in HBM (1.2 GB per GPU, > 126 MB L2: no flush needed)",
+                       "output": "float32 [n,4]", "fabrik_precision": "fp64 iterate + fp64 angle extraction",
+                       "mean_iterations": total.sum_iterations / (n * world),
+                       "iteration_capped_fraction": total.n_iter_capped / (n * world),
+                       "sharding": f"contiguous ranges, {world} rank(s), no data-path collective"},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(gpu_launches), "roofline": roofline,
+            "cpu_baseline": cpu_baseline, "fk_error": fk_error, "fabrik_interior_box": interior, "ann": ann_block,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -265,6 +265,7 @@ int ikb_engine_create(const ikb_config *cfg, ikb_engine **out)
         }
         if (status != 0)
             rc.planar = 0;
+        rc.seed_ab = std::sqrt(rc.seed_r[0] * rc.seed_r[0] + rc.seed_z[0] * rc.seed_z[0]);
     }
     *out = e;
     return IKB_OK;

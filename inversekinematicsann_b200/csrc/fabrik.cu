@@ -127,6 +127,53 @@ __device__ __forceinline__ double round8(double x)
     return fma(fma(-r, 1e8, q), 1e-8, r);
 }
 
+// asin(s) for 0 <= s <= 0.5 given t = s^2: s + s t P(t), P fitted by tools/fit_asin_poly.py
+// (degree 9, max abs error 1.2e-15).  Shared core of the acos / atan2 replacements below: the CUDA
+// library versions cost ~4x more instructions and the epilogue is the second largest consumer of
+// issue slots in this kernel.
+__constant__ double c_asin_poly[10] = {
+    0.16666666666025234, 0.07500000093993356, 0.04464280537685713, 0.03038341968562146,
+    0.022347394121891163, 0.017613143412093663, 0.012211296489012176, 0.01903265892950786,
+    -0.009325464322296697, 0.03306665466887422};
+
+__device__ __forceinline__ double asin_core(double s, double t)
+{
+    double p = c_asin_poly[9];  // constant-bank operands: no immediates to materialise
+#pragma unroll
+    for (int i = 8; i >= 0; --i)
+        p = fma(p, t, c_asin_poly[i]);
+    return fma(s * t, p, s);
+}
+
+// acos(c), |c| <= 1 (NaN outside, like math.acos raising ValueError upstream); abs error < 3e-15.
+// |c| <= 1/2: pi/2 - asin(c);  otherwise 2 asin(sqrt((1 - |c|) / 2)), reflected for c < 0.
+__device__ __forceinline__ double acos_fast(double c)
+{
+    const double PI = 3.141592653589793;
+    const double a = fabs(c);
+    const bool small = a <= 0.5;
+    const double t = small ? c * c : fma(-0.5, a, 0.5);
+    const double s = small ? a : fast_sqrt(t);
+    const double r = asin_core(s, t);
+    const double big = c > 0.0 ? 2.0 * r : PI - 2.0 * r;
+    return small ? PI / 2 - copysign(r, c) : big;
+}
+
+// atan2(uy, ux) for a UNIT vector (ux, uy); abs error < 3e-15.  The angle to the x axis comes from
+// asin(|uy|) when |uy| <= 1/2, from pi/2 - asin(|ux|) when |ux| <= 1/2, else from the half-angle form.
+__device__ __forceinline__ double atan2_unit(double uy, double ux)
+{
+    const double PI = 3.141592653589793;
+    const double ay = fabs(uy), ax = fabs(ux);
+    const bool m0 = ay <= 0.5, m1 = ax <= 0.5;
+    const double t = m0 ? ay * ay : (m1 ? ax * ax : fma(-0.5, ax, 0.5));
+    const double s = m0 ? ay : (m1 ? ax : fast_sqrt(t));
+    const double r = asin_core(s, t);
+    double phi = m0 ? r : (m1 ? PI / 2 - r : 2.0 * r);
+    phi = ux < 0.0 ? PI - phi : phi;
+    return copysign(phi, uy);
+}
+
 // In-plane radius of a target and the unit direction of its vertical plane.  Targets on the z axis
 // have no direction (the reference's theta_1 is rounding noise there): +x is used.
 __device__ __forceinline__ double planar_radius(double x, double y, double &ux, double &uy)
@@ -170,8 +217,10 @@ __device__ __forceinline__ void fabrik_epilogue(const FabrikArgs &a, int idx, in
     const bool finite_in = isfinite(x) & isfinite(y) & isfinite(z);
     zero_div |= finite_in & !(isfinite(r1) & isfinite(z1) & isfinite(r2) & isfinite(z2));
     double th[4];
-    th[0] = atan2(r3 * uy, r3 * ux);                                    // inverse.py:60
-    const double ab = fast_sqrt(R0 * R0 + Z0 * Z0);                      // A = origin
+    // theta_1 = atan2(E.y, E.x) with E = r3 (ux, uy) (inverse.py:60): only the sign of r3 matters
+    th[0] = r3 < 0.0 ? atan2_unit(-uy, -ux) : atan2_unit(uy, ux);
+    th[0] = r3 == 0.0 ? 0.0 : (r3 != r3 ? r3 : th[0]);
+    const double ab = rc.seed_ab;                                        // |AB|, A = origin: a constant
     const double bc = dist2d(R0, Z0, r1, z1), cd = dist2d(r1, z1, r2, z2);
     const double de = dist2d(r2, z2, r3, z3);
     const double ac = fast_sqrt(r1 * r1 + z1 * z1);
@@ -179,16 +228,16 @@ __device__ __forceinline__ void fabrik_epilogue(const FabrikArgs &a, int idx, in
     double den = 2 * ab * bc;
     zero_div |= (den == 0.0);
     const double c2 = round8(fast_div(ab * ab + bc * bc - ac * ac, den));   // inverse.py:77-81
-    const double acos2 = acos(c2);
+    const double acos2 = acos_fast(c2);
     th[1] = ((r1 * ux) * (r2 * ux) < 0) ? (3 * PI / 2) - acos2 : -(PI / 2 - acos2);  // :82-85
     den = 2 * bc * cd;
     zero_div |= (den == 0.0);
     const double c3 = round8(fast_div(bc * bc + cd * cd - bd * bd, den));   // :90-92
-    th[2] = -(PI - acos(c3));                                            // :93
+    th[2] = -(PI - acos_fast(c3));                                            // :93
     den = 2 * cd * de;
     zero_div |= (den == 0.0) | (ce == 0.0);
     const double c4 = round8(fast_div(cd * cd + de * de - ce * ce, den));   // :98-100
-    const double acos4 = acos(c4);
+    const double acos4 = acos_fast(c4);
     // t4_point_bt = PB(C, E, |CE| / 2) (inverse.py:102): (|CE|/2)/|CE| is exactly 0.5
     const double mr = r1 + 0.5 * (r3 - r1), mz = z1 + 0.5 * (z3 - z1);
     const double dista = dist2d(R0, Z0, mr, mz);

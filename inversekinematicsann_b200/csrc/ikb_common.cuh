@@ -18,6 +18,7 @@ struct IkbRobot {
     // through the z axis and the whole solve is 2-D in (r, z).
     double seed_r[4], seed_z[4];
     double seed_xyz[12];  // the theta_1 = 0 chain in 3-D (generic path)
+    double seed_ab;       // distance origin -> first joint (|AB| of inverse.py:68)
     double links[4];      // joints_distances
     double limits[6];     // xlo, xhi, ylo, yhi, zlo, zhi
     double tol;
