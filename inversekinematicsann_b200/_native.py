@@ -7,7 +7,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libikb200.so")
+LIB_PATH = os.environ.get("IKB200_LIB") or os.path.join(_HERE, "csrc", "libikb200.so")  # override: A/B builds
 
 IKB_OK = 0
 IKB_ERR_INVALID, IKB_ERR_CUDA, IKB_ERR_NO_MODEL, IKB_ERR_UNSUPPORTED = -1, -2, -3, -4

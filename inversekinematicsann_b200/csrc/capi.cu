@@ -237,6 +237,14 @@ int ikb_engine_create(const ikb_config *cfg, ikb_engine **out)
     for (int j = 0; j < 6; ++j)
         rc.limits[j] = cfg->limits[j];
     rc.tol = cfg->tol;
+    for (int j = 0; j < 2; ++j) {
+        const double d = cfg->links[j == 0 ? 0 : 3];
+        const double lo = d - cfg->tol, hi = d + cfg->tol;
+        rc.band_lo2[j] = lo > 0.0 ? lo * lo : -1.0;  // -1: every squared length is above the lower edge
+        rc.band_hi2[j] = hi * hi;
+        rc.band_lo2_f[j] = (float)rc.band_lo2[j];
+        rc.band_hi2_f[j] = (float)rc.band_hi2[j];
+    }
     rc.max_iter = cfg->max_iter;
     rc.zero_iter = (!(1.0 > cfg->tol) || cfg->max_iter <= 0) ? 1 : 0;  // fabrik.py:54-59
     // seed chain: FK of [0, dh[0][1], dh[0][2], dh[0][3]] on the device (inverse.py:123-130)

@@ -21,6 +21,9 @@
 #define IKB_FABRIK_CHUNK 256
 #define IKB_FABRIK_WARPS 8
 #define IKB_Q 64  // per-warp queue capacity (ring), power of two
+#ifndef IKB_FABRIK_MIN_CTAS
+#define IKB_FABRIK_MIN_CTAS 3
+#endif
 
 namespace {
 
@@ -47,17 +50,22 @@ struct PlanarChain {
 // forms differ only when n2 sits within an ulp of a band edge (probability ~1e-13 per test in fp64).
 template <typename Real>
 struct Band {
-    Real lo2, hi2;
-    __device__ __forceinline__ Band(double d, double tol)
-    {
-        const double lo = d - tol > 0.0 ? d - tol : 0.0, hi = d + tol;
-        lo2 = (Real)(lo * lo);
-        hi2 = (Real)(hi * hi);
-        if (!(d - tol > 0.0))
-            lo2 = (Real)-1;  // any n2 >= 0 is above the lower edge
-    }
+    Real lo2, hi2;  // precomputed on the host (IkbRobot::band_*): kernel-parameter constants
     __device__ __forceinline__ bool outside(Real n2) const { return (n2 < lo2) | (n2 > hi2); }
 };
+
+template <typename Real>
+__device__ __forceinline__ Band<Real> make_band(const IkbRobot &rc, int which);
+template <>
+__device__ __forceinline__ Band<double> make_band<double>(const IkbRobot &rc, int which)
+{
+    return Band<double>{rc.band_lo2[which], rc.band_hi2[which]};
+}
+template <>
+__device__ __forceinline__ Band<float> make_band<float>(const IkbRobot &rc, int which)
+{
+    return Band<float>{rc.band_lo2_f[which], rc.band_hi2_f[which]};
+}
 
 // One forward-and-backward-reaching pass (reference fabrik.py:60-63) in the (r, z) plane.
 // Returns true when the reference's loop condition (start_error > tol or goal_error > tol) holds.
@@ -256,22 +264,30 @@ __device__ __forceinline__ void fabrik_epilogue(const FabrikArgs &a, int idx, in
 }
 
 template <typename Real>
-__global__ void __launch_bounds__(IKB_FABRIK_WARPS * 32, 3) fabrik_planar_kernel(const FabrikArgs a)
-{
-    // per-warp rings: input queue (pre-staged targets) and output queue (parked solved chains)
-    __shared__ int s_in_idx[IKB_FABRIK_WARPS][IKB_Q];
-    __shared__ Real s_in_tr[IKB_FABRIK_WARPS][IKB_Q];
-    __shared__ Real s_in_tz[IKB_FABRIK_WARPS][IKB_Q];
-    __shared__ int s_out_idx[IKB_FABRIK_WARPS][IKB_Q];
-    __shared__ int s_out_k[IKB_FABRIK_WARPS][IKB_Q];
-    __shared__ Real s_out_c[IKB_FABRIK_WARPS][4][IKB_Q];
+struct WarpQueues {
+    int in_idx[IKB_Q];
+    Real in_tr[IKB_Q], in_tz[IKB_Q];
+    int out_idx[IKB_Q];
+    int out_k[IKB_Q];  // iterations; bit 30 set when the chain stopped on max_iter, not on the tolerance
+    Real out_c[4][IKB_Q];
+};
 
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#define IKB_CAPPED_BIT 0x40000000
+
+template <typename Real>
+__global__ void __launch_bounds__(IKB_FABRIK_WARPS * 32, IKB_FABRIK_MIN_CTAS) fabrik_planar_kernel(const FabrikArgs a)
+{
+    // per-warp rings: input queue (pre-staged targets) and output queue (parked solved chains);
+    // one struct per warp so every access is "warp base + constant + slot"
+    __shared__ WarpQueues<Real> s_queues[IKB_FABRIK_WARPS];
+
+    const int lane = threadIdx.x & 31;
+    WarpQueues<Real> &q = s_queues[threadIdx.x >> 5];
     const unsigned lt = ikb_lanemask_lt();
     const IkbRobot &rc = a.rc;
     const Real R0 = (Real)rc.seed_r[0], Z0 = (Real)rc.seed_z[0];
     const Real d1 = (Real)rc.links[1], d2 = (Real)rc.links[2];
-    const Band<Real> start_band(rc.links[0], rc.tol), goal_band(rc.links[3], rc.tol);
+    const Band<Real> start_band = make_band<Real>(rc, 0), goal_band = make_band<Real>(rc, 1);
     const int max_iter = rc.max_iter;
     const bool zero_iter = rc.zero_iter != 0;
 
@@ -306,9 +322,9 @@ __global__ void __launch_bounds__(IKB_FABRIK_WARPS * 32, 3) fabrik_planar_kernel
                     double x, y, z, ux, uy;
                     ikb_load_xyz(a.xyz, a.xyz_f64, cur + lane, x, y, z);
                     const int slot = (in_head + in_cnt + lane) & (IKB_Q - 1);
-                    s_in_idx[w][slot] = (int)(cur + lane);
-                    s_in_tr[w][slot] = (Real)planar_radius(x, y, ux, uy);
-                    s_in_tz[w][slot] = (Real)z;
+                    q.in_idx[slot] = (int)(cur + lane);
+                    q.in_tr[slot] = (Real)planar_radius(x, y, ux, uy);
+                    q.in_tz[slot] = (Real)z;
                 }
                 in_cnt += m;
                 cur += m;
@@ -321,9 +337,9 @@ __global__ void __launch_bounds__(IKB_FABRIK_WARPS * 32, 3) fabrik_planar_kernel
             const int rank = __popc(need & lt);
             if (!active && rank < in_cnt) {
                 const int slot = (in_head + rank) & (IKB_Q - 1);
-                idx = s_in_idx[w][slot];
-                Tr = s_in_tr[w][slot];
-                Tz = s_in_tz[w][slot];
+                idx = q.in_idx[slot];
+                Tr = q.in_tr[slot];
+                Tz = q.in_tz[slot];
                 c.r1 = (Real)rc.seed_r[1]; c.z1 = (Real)rc.seed_z[1];
                 c.r2 = (Real)rc.seed_r[2]; c.z2 = (Real)rc.seed_z[2];
                 k = 0;
@@ -341,6 +357,7 @@ __global__ void __launch_bounds__(IKB_FABRIK_WARPS * 32, 3) fabrik_planar_kernel
         if (active_mask != 0) {
             const int idle_limit = (exhausted && in_cnt == 0) ? 33 : IKB_FABRIK_IDLE_T;
             int n_idle = 32 - __popc(active_mask);
+            bool leave = false;
             do {
                 bool more = false;
                 if (!zero_iter) {
@@ -352,21 +369,19 @@ __global__ void __launch_bounds__(IKB_FABRIK_WARPS * 32, 3) fabrik_planar_kernel
                 if (m != 0) {
                     if (fin) {
                         const int slot = (out_head + out_cnt + __popc(m & lt)) & (IKB_Q - 1);
-                        s_out_idx[w][slot] = idx;
-                        s_out_k[w][slot] = k;
-                        s_out_c[w][0][slot] = c.r1; s_out_c[w][1][slot] = c.z1;
-                        s_out_c[w][2][slot] = c.r2; s_out_c[w][3][slot] = c.z2;
-                        iters_local += (unsigned)k;
-                        ++solved_local;
-                        capped_local += (more ? 1u : 0u);
+                        q.out_idx[slot] = idx;
+                        q.out_k[slot] = more ? (k | IKB_CAPPED_BIT) : k;
+                        q.out_c[0][slot] = c.r1; q.out_c[1][slot] = c.z1;
+                        q.out_c[2][slot] = c.r2; q.out_c[3][slot] = c.z2;
                         active = false;
                     }
                     const int nf = __popc(m);
                     out_cnt += nf;
                     n_idle += nf;
                     active_mask &= ~m;
+                    leave = (n_idle >= idle_limit) | (out_cnt >= 32) | (active_mask == 0);
                 }
-            } while (n_idle < idle_limit && out_cnt < 32 && active_mask != 0);
+            } while (!leave);
             __syncwarp();
         }
         // 4. the fp64 epilogue runs on a full warp of parked chains (or on the remainder once all
@@ -377,9 +392,12 @@ __global__ void __launch_bounds__(IKB_FABRIK_WARPS * 32, 3) fabrik_planar_kernel
             const int n_take = min(32, out_cnt);
             if (lane < n_take) {
                 const int slot = (out_head + lane) & (IKB_Q - 1);
-                fabrik_epilogue(a, s_out_idx[w][slot], s_out_k[w][slot], (double)s_out_c[w][0][slot],
-                                (double)s_out_c[w][1][slot], (double)s_out_c[w][2][slot],
-                                (double)s_out_c[w][3][slot]);
+                const int k_raw = q.out_k[slot], k_done = k_raw & (IKB_CAPPED_BIT - 1);
+                fabrik_epilogue(a, q.out_idx[slot], k_done, (double)q.out_c[0][slot], (double)q.out_c[1][slot],
+                                (double)q.out_c[2][slot], (double)q.out_c[3][slot]);
+                iters_local += (unsigned)k_done;
+                ++solved_local;
+                capped_local += (k_raw & IKB_CAPPED_BIT) ? 1u : 0u;
             }
             out_head = (out_head + n_take) & (IKB_Q - 1);
             out_cnt -= n_take;

@@ -22,6 +22,9 @@ struct IkbRobot {
     double links[4];      // joints_distances
     double limits[6];     // xlo, xhi, ylo, yhi, zlo, zhi
     double tol;
+    // convergence bands on squared lengths (start end: links[0], goal end: links[3]), see fabrik.cu
+    double band_lo2[2], band_hi2[2];
+    float band_lo2_f[2], band_hi2_f[2];  // the same edges rounded to fp32 (fp32 iterate mode)
     int max_iter;
     int planar;
     int zero_iter;        // tol >= 1 or max_iter <= 0: the reference's while loop never runs

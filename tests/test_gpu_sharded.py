@@ -1,0 +1,66 @@
+"""Sharded FABRIK ikine over two ranks (gloo rendezvous, both ranks drive cuda:0 with independent
+kernels -- no kernel waits on another) equals the single-process result row for row, and the
+reference's whole-batch exception is raised on every rank."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, out_dir):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), IKB_DEVICE="0")
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from inversekinematicsann_b200.kinematics.inverse import FabrikInverseKinematics
+    from inversekinematicsann_b200.robot.robot import OutOfRobotReachException, SixDOFRobot as R
+    from inversekinematicsann_b200.sharding import ShardedFabrik
+    ik = FabrikInverseKinematics(R.dh_matrix, R.links_lengths, R.effector_workspace_limits, device=0)
+    rng = np.random.RandomState(17)
+    pts = rng.rand(30_001, 3) * [6, 12, 9] + [0, -6, -3]
+    full = ShardedFabrik(ik).ikine(pts)
+    if rank == 0:
+        np.save(os.path.join(out_dir, "sharded.npy"), full)
+        np.save(os.path.join(out_dir, "iters.npy"), np.array([ik.last_stats.sum_iterations, ik.last_stats.n_solved]))
+    else:
+        assert full is None
+    bad = pts.copy()
+    bad[29_000, 2] = 6.5  # lives in rank 1's shard: both ranks must raise, with the global row
+    try:
+        ShardedFabrik(ik).ikine(bad)
+        raised = ""
+    except OutOfRobotReachException as exc:
+        raised = str(exc)
+    with open(os.path.join(out_dir, f"raised{rank}.txt"), "w") as f:
+        f.write(raised)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_sharded_fabrik(tmp_path):
+    from inversekinematicsann_b200.kinematics.inverse import FabrikInverseKinematics
+    from inversekinematicsann_b200.robot.robot import SixDOFRobot as R
+    mp.spawn(_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
+    rng = np.random.RandomState(17)
+    pts = rng.rand(30_001, 3) * [6, 12, 9] + [0, -6, -3]
+    ik = FabrikInverseKinematics(R.dh_matrix, R.links_lengths, R.effector_workspace_limits)
+    single = ik.ikine(pts, as_array=True)
+    sharded = np.load(tmp_path / "sharded.npy")
+    assert np.array_equal(single, sharded, equal_nan=True)
+    its = np.load(tmp_path / "iters.npy")
+    assert its[0] == ik.last_stats.sum_iterations and its[1] == 30_001
+    for r in range(2):
+        msg = open(tmp_path / f"raised{r}.txt").read()
+        assert "is out of manipulator reach area" in msg and "6.5" in msg

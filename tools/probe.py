@@ -50,7 +50,7 @@ def main():
     m = int(os.environ.get("PROBE_M", 1_000_000))
     xyz = u[:m] * torch.tensor(boxes["W"][0], device="cuda") + torch.tensor(boxes["W"][1], device="cuda")
     ang = torch.empty(m, 4, device="cuda")
-    for mode in os.environ.get("PROBE_MODES", "fp32").split(","):
+    for mode in [x for x in os.environ.get("PROBE_MODES", "fp32").split(",") if x != "none"]:
         best, med = timed(lambda: eng.ann_solve_device(xyz, ang, mode=mode), reps=3, warm=1)
         out[f"mlp_{mode}"] = {"solves_per_s": m / best, "ms": best * 1e3, "tflops": m * 2 * eng.mlp_macs_per_row / best / 1e12}
     print(json.dumps(out, indent=1))
