@@ -217,6 +217,8 @@ void ikb_mlp_free(IkbMlp &m)
         cudaFree(m.arena);
     m.arena = nullptr;
     m.loaded = false;
+    ikb_mlp_tc_delete(m.tc);
+    m.tc = nullptr;
 }
 
 int ikb_mlp_upload(IkbMlp &m, int n_layers, const int *dims, const float *const *weights,
@@ -287,6 +289,12 @@ int ikb_mlp_upload(IkbMlp &m, int n_layers, const int *dims, const float *const 
         d.mean_y[j] = (float)mean_y[j];  // sklearn casts scale_/mean_ to the fp32 array's dtype
         d.scale_y[j] = (float)scale_y[j];
     }
+    m.tc = ikb_mlp_tc_new();
+    {
+        const int rc = ikb_mlp_tc_pack(*m.tc, n_layers, dims, weights, biases, mean_x, scale_x, mean_y, scale_y, err);
+        if (rc != IKB_OK)
+            return rc;
+    }
     m.dev = d;
     m.arena_bytes = total;
     m.macs_per_row = macs;
@@ -310,9 +318,15 @@ int ikb_mlp_launch(const IkbMlp &m, const void *xyz, int xyz_f64, long long n, l
     launches = 0;
     if (n <= 0)
         return IKB_OK;
+    if (mode == IKB_MLP_FP16X3_TC) {
+        const int rc_tc = ikb_mlp_tc_launch(*m.tc, xyz, xyz_f64, n, index_base, angles_out, stats, rc, num_sms,
+                                            stream, err);
+        launches = rc_tc == IKB_OK ? 1 : 0;
+        return rc_tc;
+    }
     if (mode != IKB_MLP_FP32_SIMT) {
-        err = "ikb_ann_solve: IKB_MLP_FP16X3_TC is not built into this library version";
-        return IKB_ERR_UNSUPPORTED;
+        err = "ikb_ann_solve: unknown MLP mode";
+        return IKB_ERR_INVALID;
     }
     MlpArgs a;
     a.xyz = xyz; a.xyz_f64 = xyz_f64; a.n = n; a.index_base = index_base; a.out = angles_out;

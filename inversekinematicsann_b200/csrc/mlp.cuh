@@ -20,8 +20,19 @@ struct IkbMlpDevice {
     float mean_y[4], scale_y[4];        // StandardScaler.inverse_transform on the fp32 output
 };
 
+struct IkbMlpTc;  // tensor-core packing of the same network (mlp_tc.cu)
+IkbMlpTc *ikb_mlp_tc_new();
+void ikb_mlp_tc_delete(IkbMlpTc *t);
+int ikb_mlp_tc_pack(IkbMlpTc &t, int n_layers, const int *dims, const float *const *weights,
+                    const float *const *biases, const double mean_x[3], const double scale_x[3],
+                    const double mean_y[4], const double scale_y[4], std::string &err);
+int ikb_mlp_tc_launch(const IkbMlpTc &t, const void *xyz, int xyz_f64, long long n, long long index_base,
+                      float *angles_out, IkbDeviceStats *stats, const IkbRobot &rc, int num_sms,
+                      cudaStream_t stream, std::string &err);
+
 struct IkbMlp {
     bool loaded = false;
+    IkbMlpTc *tc = nullptr;
     IkbMlpDevice dev;
     void *arena = nullptr;  // one device allocation holding all padded weights and biases
     size_t arena_bytes = 0;

@@ -1,0 +1,552 @@
+// mlp_tc.cu -- K2 on the 5th-generation tensor cores (IKB_MLP_FP16X3_TC), sm_100a only.
+//
+// Same contract as mlp.cu (reference ann.py:70-76 behind inverse.py:152-155), fp32-grade results from
+// fp16 tensor-core MMAs by splitting BOTH operands:  x = x_hi + x_lo,  w = w_hi + w_lo  (fp16 each, the lo
+// parts rescaled into the normal range), fp32 accumulation in TMEM.  All four partial products are formed.
+//
+// Formulation (transposed so that hi/lo partial sums share a TMEM lane):
+//   D[f, n] = sum_k Wt[f, k] * Xs[n, k]       f = output feature (UMMA M = 128 = TMEM lane)
+//                                             n = stacked batch row: n < 64 -> x_hi of row n,
+//                                                 n >= 64 -> 2^11 * x_lo of row n - 64   (UMMA N = 128)
+//   A operand = weight tile [128 features x 64 k] (w_hi then w_lo, both accumulate into the same D),
+//   B operand = activation granule [128 stacked rows x 64 k]; both K-major, 128-byte swizzle.
+//   pre-activation(row j, f) = (D[f, j] + 2^-11 D[f, 64 + j]) / s_w + bias[f]
+// One persistent CTA owns 64 targets.  Their activations never leave shared memory: a ring of
+// (K/64 + 2) granules of 16 KB; the epilogue of feature tile ft writes the two granules of the next
+// layer's input that its 128 features make up.  Weights (L2 resident, pre-swizzled on the host) stream
+// through a 4 x 16 KB ring filled by the TMA engine (cp.async.bulk).  D uses all 512 TMEM columns, one
+// 128-column accumulator per feature tile, so the epilogue of tile ft overlaps the MMAs of tile ft + 1.
+//
+// Warp roles: warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer (one elected thread each),
+// warps 2..9 = epilogue (two warps per TMEM sub-partition, 32 batch rows each).
+// The 3-input first layer and the 4-output last layer are CUDA-core work inside the epilogue warps.
+#include <cuda_fp16.h>
+
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+#include "mlp.cuh"
+
+namespace {
+
+constexpr int ROWS = 64;             // targets per CTA tile
+constexpr int GRAN_BYTES = 16384;    // 128 stacked rows x 64 k x fp16
+constexpr int W_STAGES = 4;
+constexpr int N_EPI_WARPS = 8;
+constexpr int THREADS = (2 + N_EPI_WARPS) * 32;
+constexpr float LO_SCALE = 2048.0f;  // x_lo is stored times 2^11 (kept in the normal fp16 range)
+constexpr float LO_UNSCALE = 1.0f / 2048.0f;
+
+struct TcNet {
+    int n_mma_layers;        // hidden layers 2..NH (tensor cores)
+    int hp;                  // common padded hidden width (multiple of 128)
+    const __half *w_tiles;   // [n_mma_layers][NT][KG][hi|lo][128 x 64 swizzled]
+    const float *w_first;    // [3][hp] (layer 1 kernel), fp32
+    const float *b_hidden;   // [1 + n_mma_layers][hp]
+    const float *inv_sw;     // [n_mma_layers]  1 / (power-of-two weight scale)
+    const float *w_last;     // [hp][4]
+    float b_last[4];
+    double mean_x[3], scale_x[3];
+    float mean_y[4], scale_y[4];
+};
+
+struct TcArgs {
+    const void *xyz;
+    int xyz_f64;
+    long long n;
+    long long index_base;
+    float *out;
+    IkbDeviceStats *stats;
+    IkbRobot rc;
+    TcNet net;
+};
+
+// ---- PTX helpers ----------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "TC_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra TC_DONE;\n"
+        "bra TC_WAIT;\n"
+        "TC_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// K-major, 128-byte-swizzle shared-memory matrix descriptor (8-row groups 1024 B apart)
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr)
+{
+    return (uint64_t)((smem_addr >> 4) & 0x3FFF) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+
+// D[tmem] (+)= A[smem] * B[smem], kind::f16 (fp16 inputs, fp32 accumulate), M = 128, N = 128, K = 16
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                         uint32_t accumulate)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t *bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+// 32 lanes x 32 columns of fp32 accumulators -> 32 registers per thread (thread = TMEM lane)
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32])
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// tanh(x) = sign(x) (1 - e) / (1 + e), e = 2^(-2 |x| log2 e): two MUFU ops, absolute error ~1e-7
+__device__ __forceinline__ float fast_tanh(float x)
+{
+    const float e = exp2f(-2.8853900817779268f * fabsf(x));
+    const float t = __fdividef(1.0f - e, 1.0f + e);
+    return copysignf(t, x);
+}
+
+// byte offset of element (row, k) inside a [rows x 64] fp16 K-major tile with the 128-byte swizzle
+__device__ __host__ __forceinline__ int swz_off(int row, int k)
+{
+    return row * 128 + ((((k >> 3) ^ (row & 7)) & 7) << 4) + ((k & 7) << 1);
+}
+
+// split y into fp16 hi and 2^11-scaled fp16 lo, stored for batch row `row` at feature column kcol
+__device__ __forceinline__ void store_split(unsigned char *granule, int row, int kcol, float y)
+{
+    const __half hi = __float2half_rn(y);
+    const __half lo = __float2half_rn((y - __half2float(hi)) * LO_SCALE);
+    *reinterpret_cast<__half *>(granule + swz_off(row, kcol)) = hi;
+    *reinterpret_cast<__half *>(granule + swz_off(ROWS + row, kcol)) = lo;
+}
+
+__global__ void __launch_bounds__(THREADS, 1) mlp_tc_kernel(const TcArgs a)
+{
+    extern __shared__ __align__(1024) unsigned char smem[];
+    const TcNet &net = a.net;
+    const int HP = net.hp, NT = HP >> 7, KG = HP >> 6, R = KG + 2, NM = net.n_mma_layers;
+    unsigned char *ring = smem;                                  // R granules
+    unsigned char *wring = smem + (size_t)R * GRAN_BYTES;         // W_STAGES tiles of 16 KB
+    unsigned char *misc = wring + (size_t)W_STAGES * GRAN_BYTES;
+    float *s_xs = reinterpret_cast<float *>(misc);                // [64][3] scaled inputs
+    float *s_out = s_xs + ROWS * 4;                               // [64][4] outputs
+    uint64_t *bars = reinterpret_cast<uint64_t *>(s_out + ROWS * 4);
+    uint64_t *w_full = bars, *w_empty = bars + W_STAGES;          // TMA <-> MMA
+    uint64_t *d_full = w_empty + W_STAGES, *d_empty = d_full + 4; // MMA <-> epilogue, per feature tile
+    uint64_t *act_full = d_empty + 4;                             // epilogue -> MMA, per ring slot (<= 10)
+    uint64_t *layer_done = act_full + 10;                         // MMA -> epilogue: input granules are free
+    uint32_t *s_tmem = reinterpret_cast<uint32_t *>(layer_done + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < W_STAGES; ++i) {
+            mbar_init(&w_full[i], 1);
+            mbar_init(&w_empty[i], 1);
+        }
+        for (int i = 0; i < 4; ++i) {
+            mbar_init(&d_full[i], 1);
+            mbar_init(&d_empty[i], N_EPI_WARPS);
+        }
+        for (int i = 0; i < 10; ++i)
+            mbar_init(&act_full[i], N_EPI_WARPS / 2);  // one granule is written by 4 epilogue warps
+        mbar_init(layer_done, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {  // TMEM: all 512 columns (4 accumulators of 128 columns)
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "r"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *s_tmem;
+
+    const long long n_tiles = (a.n + ROWS - 1) / ROWS;
+
+    if (warp == 0) {
+        // ===== TMA producer: weight tiles in consumption order (layer, feature tile, k chunk, hi|lo) =====
+        if (lane == 0) {
+            uint32_t cnt = 0;
+            const size_t tiles_per_net = (size_t)NM * NT * KG * 2;
+            for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                const unsigned char *src = reinterpret_cast<const unsigned char *>(net.w_tiles);
+                for (size_t t = 0; t < tiles_per_net; ++t, ++cnt) {
+                    const int s = cnt % W_STAGES;
+                    mbar_wait(&w_empty[s], ((cnt / W_STAGES) & 1) ^ 1);
+                    mbar_expect_tx(&w_full[s], GRAN_BYTES);
+                    tma_load_1d(wring + (size_t)s * GRAN_BYTES, src + t * GRAN_BYTES, GRAN_BYTES, &w_full[s]);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            // instruction descriptor: D fp32, A/B fp16, both K-major, N = 128, M = 128
+            const uint32_t idesc = (1u << 4) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
+            uint32_t wcnt = 0, act_phase = 0, use = 0;  // use = running index of MMA layers (all tiles)
+            for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                for (int m = 0; m < NM; ++m, ++use) {
+                    for (int ft = 0; ft < NT; ++ft) {
+                        mbar_wait(&d_empty[ft], (use & 1) ^ 1);  // epilogue drained this accumulator
+                        tc_fence_after();
+                        const uint32_t d_tmem = tmem_base + ft * 128;
+                        for (int kc = 0; kc < KG; ++kc) {
+                            const int slot = (KG * m + kc) % R;
+                            if (ft == 0) {  // granule kc of this layer's input has been written
+                                mbar_wait(&act_full[slot], (act_phase >> slot) & 1);
+                                act_phase ^= 1u << slot;
+                                tc_fence_after();
+                            }
+                            const uint32_t b_addr = smem_u32(ring + (size_t)slot * GRAN_BYTES);
+#pragma unroll
+                            for (int part = 0; part < 2; ++part, ++wcnt) {  // w_hi tile, then w_lo tile
+                                const int s = wcnt % W_STAGES;
+                                mbar_wait(&w_full[s], (wcnt / W_STAGES) & 1);
+                                tc_fence_after();
+                                const uint32_t a_addr = smem_u32(wring + (size_t)s * GRAN_BYTES);
+#pragma unroll
+                                for (int ks = 0; ks < 4; ++ks)  // UMMA_K = 16 fp16 = 32 bytes along the swizzled row
+                                    umma_f16(d_tmem, make_desc(a_addr + ks * 32), make_desc(b_addr + ks * 32), idesc,
+                                             (kc | part | ks) != 0);
+                                umma_commit(&w_empty[s]);  // stage reusable once these MMAs have read it
+                            }
+                        }
+                        umma_commit(&d_full[ft]);
+                    }
+                    umma_commit(layer_done);
+                }
+            }
+        }
+    } else {
+        // ===== epilogue warps: thread = (feature within tile, half of the batch rows) =====
+        const int ew = warp - 2;            // 0..7
+        const int sub = warp & 3;           // TMEM sub-partition this warp may access
+        const int half = ew >> 2;           // batch rows [32 half, 32 half + 32)
+        const int f_in_tile = sub * 32 + lane;
+        const int et = ew * 32 + lane;      // 0..255
+        uint32_t use = 0;
+        for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            const long long row0 = tile * ROWS;
+            // ---- inputs: x_scaler.transform in fp64 -> fp32 (ann.py:72), workspace limits (inverse.py:154) ----
+            if (et < ROWS) {
+                const long long i = row0 + et;
+                float v0 = 0.f, v1 = 0.f, v2 = 0.f;
+                if (i < a.n) {
+                    double x, y, z;
+                    ikb_load_xyz(a.xyz, a.xyz_f64, i, x, y, z);
+                    if (ikb_out_of_limits(a.rc, x, y, z))
+                        atomicMin(&a.stats->first_out_of_limits, a.index_base + i);
+                    v0 = (float)((x - net.mean_x[0]) / net.scale_x[0]);
+                    v1 = (float)((y - net.mean_x[1]) / net.scale_x[1]);
+                    v2 = (float)((z - net.mean_x[2]) / net.scale_x[2]);
+                }
+                s_xs[et * 4 + 0] = v0; s_xs[et * 4 + 1] = v1; s_xs[et * 4 + 2] = v2;
+            }
+            asm volatile("bar.sync 1, %0;" ::"n"(N_EPI_WARPS * 32));
+            // ---- layer 1 (3 -> HP) on the CUDA cores, written as the first MMA layer's input ----
+            for (int ft = 0; ft < NT; ++ft) {
+                const int f = ft * 128 + f_in_tile;
+                const float w0 = __ldg(net.w_first + f), w1 = __ldg(net.w_first + HP + f),
+                            w2 = __ldg(net.w_first + 2 * HP + f), b = __ldg(net.b_hidden + f);
+                const int slot = (2 * ft + (f_in_tile >> 6)) % R;  // X(1) occupies slots 0 .. KG-1
+                unsigned char *g = ring + (size_t)slot * GRAN_BYTES;
+#pragma unroll 4
+                for (int r = 0; r < 32; ++r) {
+                    const int j = half * 32 + r;
+                    const float pre = fmaf(s_xs[j * 4 + 2], w2, fmaf(s_xs[j * 4 + 1], w1, fmaf(s_xs[j * 4], w0, b)));
+                    store_split(g, j, f_in_tile & 63, tanhf(pre));
+                }
+                if (NM > 0) {
+                    fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0)
+                        mbar_arrive(&act_full[slot]);
+                }
+            }
+            // ---- hidden layers 2..NH: accumulators from TMEM -> bias, tanh, split -> next layer's granules ----
+            for (int m = 0; m < NM; ++m, ++use) {
+                const float inv_sw = __ldg(net.inv_sw + m);
+                for (int ft = 0; ft < NT; ++ft) {
+                    mbar_wait(&d_full[ft], use & 1);
+                    tc_fence_after();
+                    uint32_t dh[32], dl[32];
+                    const uint32_t taddr = tmem_base + ((uint32_t)(sub * 32) << 16) + ft * 128 + half * 32;
+                    tmem_ld32(taddr, dh);          // columns of x_hi rows
+                    tmem_ld32(taddr + ROWS, dl);   // columns of x_lo rows
+                    tmem_ld_wait();
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0)
+                        mbar_arrive(&d_empty[ft]);
+                    const int f = ft * 128 + f_in_tile;
+                    const float b = __ldg(net.b_hidden + (size_t)(m + 1) * HP + f);
+                    float y[32];
+#pragma unroll
+                    for (int r = 0; r < 32; ++r) {
+                        const float acc = fmaf(__uint_as_float(dl[r]), LO_UNSCALE, __uint_as_float(dh[r]));
+                        y[r] = fast_tanh(fmaf(acc, inv_sw, b));
+                    }
+                    // granules 2 ft, 2 ft + 1 of the next input; all but the first pair reuse slots that this
+                    // layer's MMAs are still reading until the whole layer has been issued and completed
+                    if (ft > 0)
+                        mbar_wait(layer_done, use & 1);
+                    const int slot = (KG * (m + 1) + 2 * ft + (f_in_tile >> 6)) % R;
+                    unsigned char *g = ring + (size_t)slot * GRAN_BYTES;
+#pragma unroll
+                    for (int r = 0; r < 32; ++r)
+                        store_split(g, half * 32 + r, f_in_tile & 63, y[r]);
+                    if (m + 1 < NM) {
+                        fence_proxy_async();
+                        __syncwarp();
+                        if (lane == 0)
+                            mbar_arrive(&act_full[slot]);
+                    }
+                }
+                if (NT == 1)  // keep layer_done's phase in step when no tile waited on it
+                    mbar_wait(layer_done, use & 1);
+            }
+            // ---- output layer (HP -> 4) + y_scaler.inverse_transform (ann.py:71-75): thread = (row, output) ----
+            asm volatile("bar.sync 1, %0;" ::"n"(N_EPI_WARPS * 32));
+            {
+                const int j = et & 63, o = et >> 6;
+                const int base_slot = (KG * NM) % R;
+                float acc = 0.f;
+                for (int kg = 0; kg < KG; ++kg) {
+                    const unsigned char *g = ring + (size_t)((base_slot + kg) % R) * GRAN_BYTES;
+#pragma unroll 2
+                    for (int c = 0; c < 8; ++c) {
+                        const uint4 hv = *reinterpret_cast<const uint4 *>(g + j * 128 + (((c ^ (j & 7)) & 7) << 4));
+                        const uint4 lv =
+                            *reinterpret_cast<const uint4 *>(g + (ROWS + j) * 128 + (((c ^ (j & 7)) & 7) << 4));
+                        const __half2 *h2 = reinterpret_cast<const __half2 *>(&hv);
+                        const __half2 *l2 = reinterpret_cast<const __half2 *>(&lv);
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const float2 hf = __half22float2(h2[q]), lf = __half22float2(l2[q]);
+                            const int k = kg * 64 + c * 8 + q * 2;
+                            acc = fmaf(fmaf(lf.x, LO_UNSCALE, hf.x), __ldg(net.w_last + k * 4 + o), acc);
+                            acc = fmaf(fmaf(lf.y, LO_UNSCALE, hf.y), __ldg(net.w_last + (k + 1) * 4 + o), acc);
+                        }
+                    }
+                }
+                float yv = acc + net.b_last[o];
+                yv = __fmul_rn(yv, net.scale_y[o]);
+                yv = __fadd_rn(yv, net.mean_y[o]);
+                s_out[j * 4 + o] = yv;
+            }
+            asm volatile("bar.sync 1, %0;" ::"n"(N_EPI_WARPS * 32));
+            if (et < ROWS && row0 + et < a.n)
+                reinterpret_cast<float4 *>(a.out)[row0 + et] = *reinterpret_cast<const float4 *>(s_out + et * 4);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+}
+
+size_t tc_smem_bytes(int hp)
+{
+    const int R = hp / 64 + 2;
+    return (size_t)R * GRAN_BYTES + (size_t)W_STAGES * GRAN_BYTES + 2 * ROWS * 4 * sizeof(float) + 32 * 8 + 64;
+}
+
+}  // namespace
+
+// ---- host side: pack the network for the tensor-core kernel ---------------------------------------------
+struct IkbMlpTc {
+    bool usable = false;
+    std::string why;
+    TcNet net;
+    void *arena = nullptr;
+};
+
+int ikb_mlp_tc_pack(IkbMlpTc &t, int n_layers, const int *dims, const float *const *weights,
+                    const float *const *biases, const double mean_x[3], const double scale_x[3],
+                    const double mean_y[4], const double scale_y[4], std::string &err)
+{
+    if (t.arena)
+        cudaFree(t.arena);
+    t.arena = nullptr;
+    t.usable = false;
+    const int nh = n_layers - 1;  // hidden layers
+    if (nh < 1) {
+        t.why = "needs at least one hidden layer";
+        return IKB_OK;
+    }
+    int hmax = 0;
+    for (int l = 1; l <= nh; ++l)
+        hmax = dims[l] > hmax ? dims[l] : hmax;
+    const int hp = ((hmax + 127) / 128) * 128;
+    const int NT = hp / 128, KG = hp / 64, NM = nh - 1;
+    const size_t tile_halfs = (size_t)128 * 64;
+    const size_t n_tiles = (size_t)NM * NT * KG * 2;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) / 256 * 256; return o; };
+    const size_t o_tiles = take(n_tiles * tile_halfs * sizeof(__half));
+    const size_t o_first = take((size_t)3 * hp * sizeof(float));
+    const size_t o_bias = take((size_t)(1 + NM) * hp * sizeof(float));
+    const size_t o_isw = take((size_t)(NM > 0 ? NM : 1) * sizeof(float));
+    const size_t o_last = take((size_t)hp * 4 * sizeof(float));
+    std::vector<unsigned char> host(off, 0);
+    __half *tiles = reinterpret_cast<__half *>(host.data() + o_tiles);
+    float *wfirst = reinterpret_cast<float *>(host.data() + o_first);
+    float *bias = reinterpret_cast<float *>(host.data() + o_bias);
+    float *isw = reinterpret_cast<float *>(host.data() + o_isw);
+    float *wlast = reinterpret_cast<float *>(host.data() + o_last);
+    for (int k = 0; k < 3; ++k)
+        for (int f = 0; f < dims[1]; ++f)
+            wfirst[(size_t)k * hp + f] = weights[0][(size_t)k * dims[1] + f];
+    for (int l = 0; l < nh; ++l)
+        for (int f = 0; f < dims[l + 1]; ++f)
+            bias[(size_t)l * hp + f] = biases[l][f];
+    for (int m = 0; m < NM; ++m) {
+        const int l = m + 1, fin = dims[l], fout = dims[l + 1];  // Keras kernel [fin][fout]
+        float wmax = 0.f;
+        for (size_t i = 0; i < (size_t)fin * fout; ++i)
+            wmax = std::fmax(wmax, std::fabs(weights[l][i]));
+        // power-of-two scale putting the largest weight near 2^13 so that w_lo stays a normal fp16 number
+        int e = 0;
+        if (wmax > 0.f)
+            e = 13 - (int)std::ceil(std::log2(wmax));
+        e = e > 24 ? 24 : (e < -8 ? -8 : e);
+        const float sw = std::ldexp(1.0f, e);
+        isw[m] = 1.0f / sw;
+        for (int ft = 0; ft < NT; ++ft)
+            for (int kc = 0; kc < KG; ++kc) {
+                __half *hi = tiles + (((size_t)(m * NT + ft) * KG + kc) * 2 + 0) * tile_halfs;
+                __half *lo = hi + tile_halfs;
+                for (int r = 0; r < 128; ++r)
+                    for (int c = 0; c < 64; ++c) {
+                        const int f = ft * 128 + r, k = kc * 64 + c;
+                        const float w = (f < fout && k < fin) ? weights[l][(size_t)k * fout + f] * sw : 0.f;
+                        const __half h = __float2half_rn(w);
+                        // TRUE low part (same scale as w_hi: both tiles accumulate into one accumulator)
+                        const __half lw = __float2half_rn(w - __half2float(h));
+                        const int o = swz_off(r, c) / 2;
+                        hi[o] = h;
+                        lo[o] = lw;
+                    }
+            }
+    }
+    {
+        const int l = nh;  // output layer
+        for (int k = 0; k < dims[l]; ++k)
+            for (int o = 0; o < 4; ++o)
+                wlast[(size_t)k * 4 + o] = weights[l][(size_t)k * 4 + o];
+    }
+    cudaError_t ce = cudaMalloc(&t.arena, off);
+    if (ce == cudaSuccess)
+        ce = cudaMemcpy(t.arena, host.data(), off, cudaMemcpyHostToDevice);
+    if (ce != cudaSuccess) {
+        err = std::string("ikb_mlp_load (tensor-core pack): ") + cudaGetErrorString(ce);
+        return IKB_ERR_CUDA;
+    }
+    TcNet &n = t.net;
+    memset(&n, 0, sizeof n);
+    n.n_mma_layers = NM;
+    n.hp = hp;
+    n.w_tiles = reinterpret_cast<const __half *>((char *)t.arena + o_tiles);
+    n.w_first = reinterpret_cast<const float *>((char *)t.arena + o_first);
+    n.b_hidden = reinterpret_cast<const float *>((char *)t.arena + o_bias);
+    n.inv_sw = reinterpret_cast<const float *>((char *)t.arena + o_isw);
+    n.w_last = reinterpret_cast<const float *>((char *)t.arena + o_last);
+    for (int o = 0; o < 4; ++o) {
+        n.b_last[o] = biases[nh][o];
+        n.mean_y[o] = (float)mean_y[o];
+        n.scale_y[o] = (float)scale_y[o];
+    }
+    for (int j = 0; j < 3; ++j) {
+        n.mean_x[j] = mean_x[j];
+        n.scale_x[j] = scale_x[j];
+    }
+    ce = cudaFuncSetAttribute(mlp_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes(hp));
+    if (ce != cudaSuccess) {
+        err = std::string("ikb_mlp_load (tensor-core smem attribute): ") + cudaGetErrorString(ce);
+        return IKB_ERR_CUDA;
+    }
+    t.usable = true;
+    return IKB_OK;
+}
+
+void ikb_mlp_tc_free(IkbMlpTc &t)
+{
+    if (t.arena)
+        cudaFree(t.arena);
+    t.arena = nullptr;
+    t.usable = false;
+}
+
+int ikb_mlp_tc_launch(const IkbMlpTc &t, const void *xyz, int xyz_f64, long long n, long long index_base,
+                      float *angles_out, IkbDeviceStats *stats, const IkbRobot &rc, int num_sms,
+                      cudaStream_t stream, std::string &err)
+{
+    if (!t.usable) {
+        err = "IKB_MLP_FP16X3_TC: this network cannot use the tensor-core path (" + t.why + ")";
+        return IKB_ERR_UNSUPPORTED;
+    }
+    TcArgs a;
+    a.xyz = xyz; a.xyz_f64 = xyz_f64; a.n = n; a.index_base = index_base; a.out = angles_out;
+    a.stats = stats; a.rc = rc; a.net = t.net;
+    const long long tiles = (n + ROWS - 1) / ROWS;
+    const unsigned grid = (unsigned)(tiles < num_sms ? tiles : num_sms);
+    mlp_tc_kernel<<<grid, THREADS, tc_smem_bytes(t.net.hp), stream>>>(a);
+    const cudaError_t ce = cudaGetLastError();
+    if (ce != cudaSuccess) {
+        err = std::string("mlp_tc_kernel launch: ") + cudaGetErrorString(ce);
+        return IKB_ERR_CUDA;
+    }
+    return IKB_OK;
+}
+
+IkbMlpTc *ikb_mlp_tc_new() { return new IkbMlpTc(); }
+void ikb_mlp_tc_delete(IkbMlpTc *t)
+{
+    if (t) {
+        ikb_mlp_tc_free(*t);
+        delete t;
+    }
+}
