@@ -2,7 +2,8 @@
 //
 // Same contract as mlp.cu (reference ann.py:70-76 behind inverse.py:152-155), fp32-grade results from
 // fp16 tensor-core MMAs by splitting BOTH operands:  x = x_hi + x_lo,  w = w_hi + w_lo  (fp16 each, the lo
-// parts rescaled into the normal range), fp32 accumulation in TMEM.  All four partial products are formed.
+// parts rescaled into the normal range), fp32 accumulation in TMEM.  Three partial products are formed
+// (x_hi w_hi, x_lo w_hi, x_hi w_lo); x_lo w_lo is ~2^-22 of the result and is dropped.
 //
 // Formulation (transposed so that hi/lo partial sums share a TMEM lane):
 //   D[f, n] = sum_k Wt[f, k] * Xs[n, k]       f = output feature (UMMA M = 128 = TMEM lane)
@@ -11,10 +12,13 @@
 //   A operand = weight tile [128 features x 64 k] (w_hi then w_lo, both accumulate into the same D),
 //   B operand = activation granule [128 stacked rows x 64 k]; both K-major, 128-byte swizzle.
 //   pre-activation(row j, f) = (D[f, j] + 2^-11 D[f, 64 + j]) / s_w + bias[f]
-// One persistent CTA owns 64 targets.  Their activations never leave shared memory: a ring of
-// (K/64 + 2) granules of 16 KB; the epilogue of feature tile ft writes the two granules of the next
-// layer's input that its 128 features make up.  Weights (L2 resident, pre-swizzled on the host) stream
-// through a 4 x 16 KB ring filled by the TMA engine (cp.async.bulk).  D uses all 512 TMEM columns, one
+// One persistent CTA owns 64 targets.  Their activations never leave shared memory: K/64 granules of
+// 16 KB, updated IN PLACE -- the epilogue of feature tile ft produces the two granules (2 ft, 2 ft + 1) of
+// the next layer's input, keeps them packed in registers, and stores them as soon as the MMA issuer
+// reports (tcgen05.commit) that the last feature tile has finished reading that granule pair.
+// Weights (L2 resident, pre-swizzled on the host) stream through a 6 x 16 KB ring filled by the TMA
+// engine (cp.async.bulk); the ring size is what bounds the stream (bytes in flight / L2 latency), which
+// is why no shared memory is spent on spare activation granules.  D uses all 512 TMEM columns, one
 // 128-column accumulator per feature tile, so the epilogue of tile ft overlaps the MMAs of tile ft + 1.
 //
 // Warp roles: warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer (one elected thread each),
@@ -28,11 +32,20 @@
 
 #include "mlp.cuh"
 
+#ifdef IKB_TC_DEBUG
+__device__ unsigned long long g_tc_dbg[16];
+#define DBG_T0() const long long _t0 = clock64()
+#define DBG_ADD(i) do { if (blockIdx.x == 0) g_tc_dbg[i] += (unsigned long long)(clock64() - _t0); } while (0)
+#else
+#define DBG_T0() do {} while (0)
+#define DBG_ADD(i) do {} while (0)
+#endif
+
 namespace {
 
 constexpr int ROWS = 64;             // targets per CTA tile
 constexpr int GRAN_BYTES = 16384;    // 128 stacked rows x 64 k x fp16
-constexpr int W_STAGES = 4;
+constexpr int W_STAGES = 6;
 constexpr int N_EPI_WARPS = 8;
 constexpr int THREADS = (2 + N_EPI_WARPS) * 32;
 constexpr float LO_SCALE = 2048.0f;  // x_lo is stored times 2^11 (kept in the normal fp16 range)
@@ -166,18 +179,18 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_tc_kernel(const TcArgs a)
 {
     extern __shared__ __align__(1024) unsigned char smem[];
     const TcNet &net = a.net;
-    const int HP = net.hp, NT = HP >> 7, KG = HP >> 6, R = KG + 2, NM = net.n_mma_layers;
-    unsigned char *ring = smem;                                  // R granules
-    unsigned char *wring = smem + (size_t)R * GRAN_BYTES;         // W_STAGES tiles of 16 KB
+    const int HP = net.hp, NT = HP >> 7, KG = HP >> 6, NM = net.n_mma_layers;
+    unsigned char *ring = smem;                                  // KG activation granules (in place)
+    unsigned char *wring = smem + (size_t)KG * GRAN_BYTES;        // W_STAGES tiles of 16 KB
     unsigned char *misc = wring + (size_t)W_STAGES * GRAN_BYTES;
     float *s_xs = reinterpret_cast<float *>(misc);                // [64][3] scaled inputs
     float *s_out = s_xs + ROWS * 4;                               // [64][4] outputs
     uint64_t *bars = reinterpret_cast<uint64_t *>(s_out + ROWS * 4);
     uint64_t *w_full = bars, *w_empty = bars + W_STAGES;          // TMA <-> MMA
     uint64_t *d_full = w_empty + W_STAGES, *d_empty = d_full + 4; // MMA <-> epilogue, per feature tile
-    uint64_t *act_full = d_empty + 4;                             // epilogue -> MMA, per ring slot (<= 10)
-    uint64_t *layer_done = act_full + 10;                         // MMA -> epilogue: input granules are free
-    uint32_t *s_tmem = reinterpret_cast<uint32_t *>(layer_done + 1);
+    uint64_t *act_full = d_empty + 4;                             // epilogue -> MMA, per granule (<= 8)
+    uint64_t *pair_free = act_full + 8;                           // MMA -> epilogue: granules 2p, 2p+1 are dead
+    uint32_t *s_tmem = reinterpret_cast<uint32_t *>(pair_free + 4);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -190,9 +203,10 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_tc_kernel(const TcArgs a)
             mbar_init(&d_full[i], 1);
             mbar_init(&d_empty[i], N_EPI_WARPS);
         }
-        for (int i = 0; i < 10; ++i)
+        for (int i = 0; i < 8; ++i)
             mbar_init(&act_full[i], N_EPI_WARPS / 2);  // one granule is written by 4 epilogue warps
-        mbar_init(layer_done, 1);
+        for (int i = 0; i < 4; ++i)
+            mbar_init(&pair_free[i], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {  // TMEM: all 512 columns (4 accumulators of 128 columns)
@@ -209,56 +223,75 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_tc_kernel(const TcArgs a)
     if (warp == 0) {
         // ===== TMA producer: weight tiles in consumption order (layer, feature tile, k chunk, hi|lo) =====
         if (lane == 0) {
-            uint32_t cnt = 0;
+            int s = 0;
+            uint32_t ph = 1;  // parity to wait for on w_empty: a fresh barrier passes a wait on parity 1
             const size_t tiles_per_net = (size_t)NM * NT * KG * 2;
             for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
                 const unsigned char *src = reinterpret_cast<const unsigned char *>(net.w_tiles);
-                for (size_t t = 0; t < tiles_per_net; ++t, ++cnt) {
-                    const int s = cnt % W_STAGES;
-                    mbar_wait(&w_empty[s], ((cnt / W_STAGES) & 1) ^ 1);
+                for (size_t t = 0; t < tiles_per_net; ++t, src += GRAN_BYTES) {
+                    { DBG_T0(); mbar_wait(&w_empty[s], ph); DBG_ADD(6); }
                     mbar_expect_tx(&w_full[s], GRAN_BYTES);
-                    tma_load_1d(wring + (size_t)s * GRAN_BYTES, src + t * GRAN_BYTES, GRAN_BYTES, &w_full[s]);
+                    tma_load_1d(wring + (size_t)s * GRAN_BYTES, src, GRAN_BYTES, &w_full[s]);
+                    if (++s == W_STAGES) {
+                        s = 0;
+                        ph ^= 1;
+                    }
                 }
             }
         }
     } else if (warp == 1) {
-        // ===== MMA issuer =====
+        // ===== MMA issuer: one thread; descriptors are base + small offsets so the issue loop stays short =====
         if (lane == 0) {
             // instruction descriptor: D fp32, A/B fp16, both K-major, N = 128, M = 128
             const uint32_t idesc = (1u << 4) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
-            uint32_t wcnt = 0, act_phase = 0, use = 0;  // use = running index of MMA layers (all tiles)
+            // w_lo only multiplies the x_hi rows (N = 64): the w_lo * x_lo term is below fp32 resolution
+            const uint32_t idesc_lo = (1u << 4) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
+            const uint64_t a_desc_base = make_desc(smem_u32(wring));
+            const uint64_t b_desc_base = make_desc(smem_u32(ring));
+            constexpr uint32_t GRAN_DESC = GRAN_BYTES >> 4;  // descriptor address units are 16 bytes
+            int s = 0;
+            uint32_t ph = 0, use = 0;  // use = running index of MMA layers over all tiles of this CTA
+#ifdef IKB_TC_DEBUG
+            const long long _tstart = clock64();
+#endif
             for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
                 for (int m = 0; m < NM; ++m, ++use) {
                     for (int ft = 0; ft < NT; ++ft) {
-                        mbar_wait(&d_empty[ft], (use & 1) ^ 1);  // epilogue drained this accumulator
+                        { DBG_T0(); mbar_wait(&d_empty[ft], (use & 1) ^ 1); DBG_ADD(3); }  // epilogue drained this accumulator
                         tc_fence_after();
                         const uint32_t d_tmem = tmem_base + ft * 128;
                         for (int kc = 0; kc < KG; ++kc) {
-                            const int slot = (KG * m + kc) % R;
                             if (ft == 0) {  // granule kc of this layer's input has been written
-                                mbar_wait(&act_full[slot], (act_phase >> slot) & 1);
-                                act_phase ^= 1u << slot;
+                                { DBG_T0(); mbar_wait(&act_full[kc], use & 1); DBG_ADD(2); }
                                 tc_fence_after();
                             }
-                            const uint32_t b_addr = smem_u32(ring + (size_t)slot * GRAN_BYTES);
+                            const uint64_t b_desc = b_desc_base + (uint64_t)(kc * GRAN_DESC);
 #pragma unroll
-                            for (int part = 0; part < 2; ++part, ++wcnt) {  // w_hi tile, then w_lo tile
-                                const int s = wcnt % W_STAGES;
-                                mbar_wait(&w_full[s], (wcnt / W_STAGES) & 1);
+                            for (int part = 0; part < 2; ++part) {  // w_hi tile, then w_lo tile
+                                { DBG_T0(); mbar_wait(&w_full[s], ph); DBG_ADD(1); }
                                 tc_fence_after();
-                                const uint32_t a_addr = smem_u32(wring + (size_t)s * GRAN_BYTES);
+                                const uint64_t a_desc = a_desc_base + (uint64_t)(s * GRAN_DESC);
 #pragma unroll
                                 for (int ks = 0; ks < 4; ++ks)  // UMMA_K = 16 fp16 = 32 bytes along the swizzled row
-                                    umma_f16(d_tmem, make_desc(a_addr + ks * 32), make_desc(b_addr + ks * 32), idesc,
+                                    umma_f16(d_tmem, a_desc + 2 * ks, b_desc + 2 * ks, part ? idesc_lo : idesc,
                                              (kc | part | ks) != 0);
                                 umma_commit(&w_empty[s]);  // stage reusable once these MMAs have read it
+                                if (++s == W_STAGES) {
+                                    s = 0;
+                                    ph ^= 1;
+                                }
                             }
+                            // the last feature tile is the last reader of the input granules: report each pair dead
+                            if (ft == NT - 1 && (kc & 1))
+                                umma_commit(&pair_free[kc >> 1]);
                         }
                         umma_commit(&d_full[ft]);
                     }
-                    umma_commit(layer_done);
                 }
             }
+#ifdef IKB_TC_DEBUG
+            if (blockIdx.x == 0) g_tc_dbg[0] += (unsigned long long)(clock64() - _tstart);
+#endif
         }
     } else {
         // ===== epilogue warps: thread = (feature within tile, half of the batch rows) =====
@@ -291,7 +324,7 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_tc_kernel(const TcArgs a)
                 const int f = ft * 128 + f_in_tile;
                 const float w0 = __ldg(net.w_first + f), w1 = __ldg(net.w_first + HP + f),
                             w2 = __ldg(net.w_first + 2 * HP + f), b = __ldg(net.b_hidden + f);
-                const int slot = (2 * ft + (f_in_tile >> 6)) % R;  // X(1) occupies slots 0 .. KG-1
+                const int slot = 2 * ft + (f_in_tile >> 6);
                 unsigned char *g = ring + (size_t)slot * GRAN_BYTES;
 #pragma unroll 4
                 for (int r = 0; r < 32; ++r) {
@@ -306,56 +339,72 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_tc_kernel(const TcArgs a)
                         mbar_arrive(&act_full[slot]);
                 }
             }
-            // ---- hidden layers 2..NH: accumulators from TMEM -> bias, tanh, split -> next layer's granules ----
+            // ---- hidden layers 2..NH: accumulators from TMEM -> bias, tanh, hi/lo split, packed in registers;
+            //      stored into the (in place) granules once the MMA issuer reports the old contents dead ----
             for (int m = 0; m < NM; ++m, ++use) {
                 const float inv_sw = __ldg(net.inv_sw + m);
-                for (int ft = 0; ft < NT; ++ft) {
-                    mbar_wait(&d_full[ft], use & 1);
-                    tc_fence_after();
-                    uint32_t dh[32], dl[32];
-                    const uint32_t taddr = tmem_base + ((uint32_t)(sub * 32) << 16) + ft * 128 + half * 32;
-                    tmem_ld32(taddr, dh);          // columns of x_hi rows
-                    tmem_ld32(taddr + ROWS, dl);   // columns of x_lo rows
-                    tmem_ld_wait();
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0)
-                        mbar_arrive(&d_empty[ft]);
-                    const int f = ft * 128 + f_in_tile;
-                    const float b = __ldg(net.b_hidden + (size_t)(m + 1) * HP + f);
-                    float y[32];
+                uint32_t packed[4][32];
+                auto flush = [&](int ft, const uint32_t (&pk)[32]) {
+                    { DBG_T0(); mbar_wait(&pair_free[ft], use & 1); if (warp == 2 && lane == 0) DBG_ADD(5); }
+                    const int slot = 2 * ft + (f_in_tile >> 6);
+                    unsigned char *g = ring + (size_t)slot * GRAN_BYTES;
+                    const int kcol = f_in_tile & 63;
 #pragma unroll
                     for (int r = 0; r < 32; ++r) {
-                        const float acc = fmaf(__uint_as_float(dl[r]), LO_UNSCALE, __uint_as_float(dh[r]));
-                        y[r] = fast_tanh(fmaf(acc, inv_sw, b));
+                        const int j = half * 32 + r;
+                        *reinterpret_cast<unsigned short *>(g + swz_off(j, kcol)) = (unsigned short)(pk[r] & 0xffffu);
+                        *reinterpret_cast<unsigned short *>(g + swz_off(ROWS + j, kcol)) = (unsigned short)(pk[r] >> 16);
                     }
-                    // granules 2 ft, 2 ft + 1 of the next input; all but the first pair reuse slots that this
-                    // layer's MMAs are still reading until the whole layer has been issued and completed
-                    if (ft > 0)
-                        mbar_wait(layer_done, use & 1);
-                    const int slot = (KG * (m + 1) + 2 * ft + (f_in_tile >> 6)) % R;
-                    unsigned char *g = ring + (size_t)slot * GRAN_BYTES;
-#pragma unroll
-                    for (int r = 0; r < 32; ++r)
-                        store_split(g, half * 32 + r, f_in_tile & 63, y[r]);
                     if (m + 1 < NM) {
                         fence_proxy_async();
                         __syncwarp();
                         if (lane == 0)
                             mbar_arrive(&act_full[slot]);
                     }
+                };
+#pragma unroll
+                for (int ft = 0; ft < 4; ++ft) {
+                    if (ft < NT) {
+                        { DBG_T0(); mbar_wait(&d_full[ft], use & 1); if (warp == 2 && lane == 0) DBG_ADD(4); }
+                        tc_fence_after();
+                        uint32_t dh[32], dl[32];
+                        const uint32_t taddr = tmem_base + ((uint32_t)(sub * 32) << 16) + ft * 128 + half * 32;
+                        tmem_ld32(taddr, dh);          // columns of the x_hi rows
+                        tmem_ld32(taddr + ROWS, dl);   // columns of the x_lo rows
+                        tmem_ld_wait();
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0)
+                            mbar_arrive(&d_empty[ft]);
+                        const float b = __ldg(net.b_hidden + (size_t)(m + 1) * HP + ft * 128 + f_in_tile);
+#pragma unroll
+                        for (int r = 0; r < 32; ++r) {
+                            const float acc = fmaf(__uint_as_float(dl[r]), LO_UNSCALE, __uint_as_float(dh[r]));
+                            const float y = fast_tanh(fmaf(acc, inv_sw, b));
+                            const __half hi = __float2half_rn(y);
+                            const __half lo = __float2half_rn((y - __half2float(hi)) * LO_SCALE);
+                            packed[ft][r] = (uint32_t)__half_as_ushort(hi) | ((uint32_t)__half_as_ushort(lo) << 16);
+                        }
+                        // pairs 0 .. NT-2 die while the last feature tile is being multiplied: flush them in order
+                        // once the second-to-last tile has been computed, the last one right after its own compute
+                        if (ft == NT - 2) {
+#pragma unroll
+                            for (int q = 0; q < 3; ++q)
+                                if (q <= ft)
+                                    flush(q, packed[q]);
+                        }
+                        if (ft == NT - 1)
+                            flush(ft, packed[ft]);
+                    }
                 }
-                if (NT == 1)  // keep layer_done's phase in step when no tile waited on it
-                    mbar_wait(layer_done, use & 1);
             }
             // ---- output layer (HP -> 4) + y_scaler.inverse_transform (ann.py:71-75): thread = (row, output) ----
             asm volatile("bar.sync 1, %0;" ::"n"(N_EPI_WARPS * 32));
             {
                 const int j = et & 63, o = et >> 6;
-                const int base_slot = (KG * NM) % R;
                 float acc = 0.f;
                 for (int kg = 0; kg < KG; ++kg) {
-                    const unsigned char *g = ring + (size_t)((base_slot + kg) % R) * GRAN_BYTES;
+                    const unsigned char *g = ring + (size_t)kg * GRAN_BYTES;
 #pragma unroll 2
                     for (int c = 0; c < 8; ++c) {
                         const uint4 hv = *reinterpret_cast<const uint4 *>(g + j * 128 + (((c ^ (j & 7)) & 7) << 4));
@@ -390,8 +439,7 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_tc_kernel(const TcArgs a)
 
 size_t tc_smem_bytes(int hp)
 {
-    const int R = hp / 64 + 2;
-    return (size_t)R * GRAN_BYTES + (size_t)W_STAGES * GRAN_BYTES + 2 * ROWS * 4 * sizeof(float) + 32 * 8 + 64;
+    return (size_t)(hp / 64) * GRAN_BYTES + (size_t)W_STAGES * GRAN_BYTES + 2 * ROWS * 4 * sizeof(float) + 40 * 8 + 64;
 }
 
 }  // namespace
@@ -550,3 +598,14 @@ void ikb_mlp_tc_delete(IkbMlpTc *t)
         delete t;
     }
 }
+
+#ifdef IKB_TC_DEBUG
+extern "C" void ikbdbg_tc_counters(unsigned long long *out, int reset)
+{
+    cudaMemcpyFromSymbol(out, g_tc_dbg, sizeof(unsigned long long) * 16);
+    if (reset) {
+        unsigned long long z[16] = {0};
+        cudaMemcpyToSymbol(g_tc_dbg, z, sizeof z);
+    }
+}
+#endif

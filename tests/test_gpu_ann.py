@@ -10,12 +10,16 @@ pytestmark = pytest.mark.gpu
 TOL_NORTH_STAR = 1e-5  # rad
 
 
-def _make(dims, seed):
+MODES = ["fp16x3", "fp32"]  # tcgen05 split-fp16 tensor-core kernel (default) and fp32 CUDA-core kernel
+
+
+def _make(dims, seed, mode="fp16x3"):
     from inversekinematicsann_b200.kinematics.inverse import AnnInverseKinematics
     from inversekinematicsann_b200.robot.robot import SixDOFRobot as R
     from oracle import np_oracle
     W, b = np_oracle.synthetic_mlp(seed=seed, dims=dims)
     ann = AnnInverseKinematics(R.dh_matrix, R.links_lengths, R.effector_workspace_limits)
+    ann.ann.mode = mode
     ann.ann.set_model(W, b, np_oracle.SHIPPED_MEAN_X, np_oracle.SHIPPED_SCALE_X,
                       np_oracle.SHIPPED_MEAN_Y, np_oracle.SHIPPED_SCALE_Y)
     return ann, W, b
@@ -26,37 +30,40 @@ def _points(n, seed=0):
     return rng.uniform([0, -6, -3], [6, 6, 6], size=(n, 3))
 
 
-def test_full_architecture_vs_fp32_oracle():
+@pytest.mark.parametrize("mode", MODES)
+def test_full_architecture_vs_fp32_oracle(mode):
     from oracle import np_oracle
-    ann, W, b = _make(np_oracle.LAYER_DIMS, seed=1234)
+    ann, W, b = _make(np_oracle.LAYER_DIMS, seed=1234, mode=mode)
     xyz = _points(20_000)
     got = ann.ikine(xyz, as_array=True)
     want32 = np_oracle.mlp_predict(xyz, W, b)
     want64 = np_oracle.mlp_predict(xyz, W, b, dtype=np.float64)
     assert got.dtype == np.float32 and got.shape == (20_000, 4)
     e32, e64 = np.abs(got - want32).max(), np.abs(got - want64).max()
-    print(f"max |dtheta| vs fp32 oracle {e32:.3e}, vs fp64 oracle {e64:.3e}, "
+    print(f"[{mode}] max |dtheta| vs fp32 oracle {e32:.3e}, vs fp64 oracle {e64:.3e}, "
           f"fp32 oracle vs fp64 oracle {np.abs(want32 - want64).max():.3e}")
     assert e32 <= TOL_NORTH_STAR and e64 <= TOL_NORTH_STAR
     as_list = ann.ikine(xyz[:3].tolist())
     assert isinstance(as_list, list) and isinstance(as_list[0][0], float)
 
 
-@pytest.mark.parametrize("n", [1, 63, 64, 65, 1000])
-@pytest.mark.parametrize("dims", [[3, 64, 4], [3, 100, 50, 4], [3, 500, 500, 500, 4]])
-def test_ragged_sizes_and_small_nets(n, dims):
+@pytest.mark.parametrize("mode", MODES)
+@pytest.mark.parametrize("n", [1, 63, 64, 65, 1000, 148 * 64 + 5])
+@pytest.mark.parametrize("dims", [[3, 64, 4], [3, 100, 50, 4], [3, 300, 300, 4], [3, 500, 500, 500, 4]])
+def test_ragged_sizes_and_small_nets(n, dims, mode):
     from oracle import np_oracle
-    ann, W, b = _make(dims, seed=7)
+    ann, W, b = _make(dims, seed=7, mode=mode)
     xyz = _points(n, seed=n)
     got = ann.ann.predict(xyz)
     want = np_oracle.mlp_predict(xyz, W, b)
     assert np.abs(got - want).max() <= TOL_NORTH_STAR
 
 
-def test_limits_and_errors():
+@pytest.mark.parametrize("mode", MODES)
+def test_limits_and_errors(mode):
     from inversekinematicsann_b200.kinematics.ann import ANN
     from inversekinematicsann_b200.robot.robot import OutOfRobotReachException, SixDOFRobot as R
-    ann, W, b = _make([3, 64, 4], seed=2)
+    ann, W, b = _make([3, 64, 4], seed=2, mode=mode)
     with pytest.raises(OutOfRobotReachException):      # reference tests/inverse_unit.py:59-62
         ann.ikine([[1.0, 2.1, 3.0], [1.567, 2.22, -3.123], [1.02, 3.33, 4.99]])
     out = ann.ann.predict([[-1.567, 2.22, -3.123]])    # predict has no limit check (ann_unit.py:39)
@@ -86,3 +93,17 @@ def test_model_files_round_trip(tmp_path):
     xyz = _points(200, seed=9)
     want = np_oracle.mlp_predict(xyz, W, b, sx.mean_, sx.scale_, sy.mean_, sy.scale_)
     assert np.abs(fresh.predict(xyz) - want).max() <= TOL_NORTH_STAR
+
+
+def test_modes_agree_and_are_deterministic():
+    """The two arithmetic modes are independent implementations of the same network: they must agree
+    with each other as well as with the oracle, and repeated launches must be bit-identical."""
+    from oracle import np_oracle
+    ann, W, b = _make(np_oracle.LAYER_DIMS, seed=99, mode="fp16x3")
+    xyz = _points(30_000, seed=5)
+    a1 = ann.ikine(xyz, as_array=True).copy()
+    a2 = ann.ikine(xyz, as_array=True).copy()
+    assert np.array_equal(a1, a2)
+    ann.ann.mode = "fp32"
+    s1 = ann.ikine(xyz, as_array=True)
+    assert np.abs(a1 - s1).max() <= TOL_NORTH_STAR
