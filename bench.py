@@ -60,7 +60,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}",
-                 "--format=csv,noheader,nounits", "-lms", "100"],
+                 "--format=csv,noheader,nounits", "-lms", "20"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except OSError:
@@ -95,6 +95,7 @@ def host_points(n, box, seed):
 def cpu_fabrik_rate(sample_rows, box, seed=1234, repeats=1):
     """solves/s of the C restatement (OpenMP, all host threads) on `sample_rows` targets."""
     from oracle import c_oracle
+    c_oracle.set_num_threads(os.cpu_count() or 1)  # torchrun exports OMP_NUM_THREADS=1 to its workers
     pts = host_points(sample_rows, box, seed)
     c_oracle.fabrik_ikine(pts[:1000])
     best = float("inf")
@@ -108,11 +109,13 @@ def cpu_fabrik_rate(sample_rows, box, seed=1234, repeats=1):
 def cpu_ann_rate(sample_rows, weights, biases, seed=1234):
     """solves/s of the NumPy fp32 restatement (BLAS threads = all host cores)."""
     from oracle import np_oracle
+    from threadpoolctl import threadpool_limits
     pts = host_points(sample_rows, WORKSPACE_BOX, seed)
-    np_oracle.mlp_predict(pts[:2048], weights, biases)
-    t0 = time.perf_counter()
-    np_oracle.mlp_predict(pts, weights, biases)
-    return sample_rows / (time.perf_counter() - t0)
+    with threadpool_limits(limits=os.cpu_count() or 1):
+        np_oracle.mlp_predict(pts[:2048], weights, biases)
+        t0 = time.perf_counter()
+        np_oracle.mlp_predict(pts, weights, biases)
+        return sample_rows / (time.perf_counter() - t0)
 
 
 def calibrated_cpu_sample(box, target_seconds=12.0):
@@ -125,6 +128,7 @@ def run_reference_arm(args, rank):
     if rank != 0:
         return
     from oracle import c_oracle
+    c_oracle.set_num_threads(os.cpu_count() or 1)
     sample, threads = calibrated_cpu_sample(WORKSPACE_BOX, target_seconds=6.0)
     pts = host_points(sample, WORKSPACE_BOX, 1234)
     for _ in range(max(1, min(args.warmup, 2))):

@@ -234,6 +234,7 @@ int ikb_engine_create(const ikb_config *cfg, ikb_engine **out)
         rc.cos_alpha[j] = std::cos(rc.alpha[j]);
         rc.sin_alpha[j] = std::sin(rc.alpha[j]);
     }
+    rc.fk_planar_tail = (rc.alpha[1] == 0.0 && rc.alpha[2] == 0.0 && rc.alpha[3] == 0.0) ? 1 : 0;
     for (int j = 0; j < 6; ++j)
         rc.limits[j] = cfg->limits[j];
     rc.tol = cfg->tol;

@@ -20,9 +20,15 @@
 
 #define IKB_FABRIK_CHUNK 256
 #define IKB_FABRIK_WARPS 8
-#define IKB_Q 64  // per-warp queue capacity (ring), power of two
+#define IKB_Q 64  // per-warp input queue capacity (ring), power of two
 #ifndef IKB_FABRIK_MIN_CTAS
 #define IKB_FABRIK_MIN_CTAS 3
+#endif
+#ifndef IKB_FABRIK_MIN_CTAS2
+#define IKB_FABRIK_MIN_CTAS2 2
+#endif
+#ifndef IKB_FABRIK_CHAINS
+#define IKB_FABRIK_CHAINS 1
 #endif
 
 namespace {
@@ -263,26 +269,32 @@ __device__ __forceinline__ void fabrik_epilogue(const FabrikArgs &a, int idx, in
         a.iters[idx] = k;
 }
 
-template <typename Real>
+// OUT_Q: parked-chain ring; < 32 entries wait when a pass starts and a pass parks at most 32 per chain slot
+template <typename Real, int OUT_Q>
 struct WarpQueues {
     int in_idx[IKB_Q];
     Real in_tr[IKB_Q], in_tz[IKB_Q];
-    int out_idx[IKB_Q];
-    int out_k[IKB_Q];  // iterations; bit 30 set when the chain stopped on max_iter, not on the tolerance
-    Real out_c[4][IKB_Q];
+    int out_idx[OUT_Q];
+    int out_k[OUT_Q];  // iterations; bit 30 set when the chain stopped on max_iter, not on the tolerance
+    Real out_c[4][OUT_Q];
 };
 
 #define IKB_CAPPED_BIT 0x40000000
 
-template <typename Real>
-__global__ void __launch_bounds__(IKB_FABRIK_WARPS * 32, IKB_FABRIK_MIN_CTAS) fabrik_planar_kernel(const FabrikArgs a)
+// CHAINS = independent chains per lane.  The pass is one long dependency chain (every instruction
+// needs the previous result), so a second chain per lane doubles the instruction-level parallelism a
+// warp offers the FP64 pipe; its cost is registers (fewer resident warps).
+template <typename Real, int CHAINS>
+__global__ void __launch_bounds__(IKB_FABRIK_WARPS * 32, (CHAINS == 1 ? IKB_FABRIK_MIN_CTAS : IKB_FABRIK_MIN_CTAS2))
+    fabrik_planar_kernel(const FabrikArgs a)
 {
     // per-warp rings: input queue (pre-staged targets) and output queue (parked solved chains);
     // one struct per warp so every access is "warp base + constant + slot"
-    __shared__ WarpQueues<Real> s_queues[IKB_FABRIK_WARPS];
+    constexpr int OUT_Q = 32 + 32 * CHAINS;
+    __shared__ WarpQueues<Real, OUT_Q> s_queues[IKB_FABRIK_WARPS];
 
     const int lane = threadIdx.x & 31;
-    WarpQueues<Real> &q = s_queues[threadIdx.x >> 5];
+    WarpQueues<Real, OUT_Q> &q = s_queues[threadIdx.x >> 5];
     const unsigned lt = ikb_lanemask_lt();
     const IkbRobot &rc = a.rc;
     const Real R0 = (Real)rc.seed_r[0], Z0 = (Real)rc.seed_z[0];
@@ -291,11 +303,16 @@ __global__ void __launch_bounds__(IKB_FABRIK_WARPS * 32, IKB_FABRIK_MIN_CTAS) fa
     const int max_iter = rc.max_iter;
     const bool zero_iter = rc.zero_iter != 0;
 
-    bool active = false, exhausted = false;
-    unsigned active_mask = 0;  // warp-uniform copy of `active`
-    int idx = 0, k = 0;
-    Real Tr = 0, Tz = 0;
-    PlanarChain<Real> c{0, 0, 0, 0};
+    bool active[CHAINS], exhausted = false;
+    unsigned active_mask[CHAINS];  // warp-uniform copies of `active`
+    int idx[CHAINS], k[CHAINS];
+    Real Tr[CHAINS], Tz[CHAINS];
+    PlanarChain<Real> c[CHAINS];
+#pragma unroll
+    for (int u = 0; u < CHAINS; ++u) {
+        active[u] = false; active_mask[u] = 0; idx[u] = 0; k[u] = 0; Tr[u] = 0; Tz[u] = 0;
+        c[u] = PlanarChain<Real>{0, 0, 0, 0};
+    }
     long long cur = 0, cur_end = 0;
     int in_head = 0, in_cnt = 0, out_head = 0, out_cnt = 0;
     unsigned long long iters_local = 0;
@@ -331,55 +348,83 @@ __global__ void __launch_bounds__(IKB_FABRIK_WARPS * 32, IKB_FABRIK_MIN_CTAS) fa
                 __syncwarp();
             }
         }
-        // 2. idle lanes take the next staged targets
-        if (active_mask != IKB_FULL_MASK && in_cnt > 0) {
-            const unsigned need = ~active_mask;
-            const int rank = __popc(need & lt);
-            if (!active && rank < in_cnt) {
-                const int slot = (in_head + rank) & (IKB_Q - 1);
-                idx = q.in_idx[slot];
-                Tr = q.in_tr[slot];
-                Tz = q.in_tz[slot];
-                c.r1 = (Real)rc.seed_r[1]; c.z1 = (Real)rc.seed_z[1];
-                c.r2 = (Real)rc.seed_r[2]; c.z2 = (Real)rc.seed_z[2];
-                k = 0;
-                active = true;
+        // 2. idle chain slots take the next staged targets
+        unsigned any_active = 0;
+#pragma unroll
+        for (int u = 0; u < CHAINS; ++u) {
+            if (active_mask[u] != IKB_FULL_MASK && in_cnt > 0) {
+                const unsigned need = ~active_mask[u];
+                const int rank = __popc(need & lt);
+                if (!active[u] && rank < in_cnt) {
+                    const int slot = (in_head + rank) & (IKB_Q - 1);
+                    idx[u] = q.in_idx[slot];
+                    Tr[u] = q.in_tr[slot];
+                    Tz[u] = q.in_tz[slot];
+                    c[u].r1 = (Real)rc.seed_r[1]; c[u].z1 = (Real)rc.seed_z[1];
+                    c[u].r2 = (Real)rc.seed_r[2]; c[u].z2 = (Real)rc.seed_z[2];
+                    k[u] = 0;
+                    active[u] = true;
+                }
+                const int take = min(__popc(need), in_cnt);
+                in_head = (in_head + take) & (IKB_Q - 1);
+                in_cnt -= take;
+                active_mask[u] = __ballot_sync(IKB_FULL_MASK, active[u]);
             }
-            const int take = min(__popc(need), in_cnt);
-            in_head = (in_head + take) & (IKB_Q - 1);
-            in_cnt -= take;
-            active_mask = __ballot_sync(IKB_FULL_MASK, active);
+            any_active |= active_mask[u];
         }
-        // 3. FABRIK passes (reference fabrik.py:57-65).  Every lane executes the pass -- lanes without a
-        //    live chain compute on stale registers and are ignored -- so the loop body is branch-free;
-        //    a lane that finishes parks its chain at once and the warp only leaves the loop when
-        //    enough lanes idle to make a refill worthwhile or a full warp of parked chains is ready.
-        if (active_mask != 0) {
-            const int idle_limit = (exhausted && in_cnt == 0) ? 33 : IKB_FABRIK_IDLE_T;
-            int n_idle = 32 - __popc(active_mask);
+        // 3. FABRIK passes (reference fabrik.py:57-65).  Every lane executes the pass -- chain slots without
+        //    a live chain compute on stale registers and are ignored -- so the loop body is branch-free;
+        //    a chain that finishes is parked at once and the warp only leaves the loop when enough slots
+        //    idle to make a refill worthwhile or a full warp of parked chains is ready.
+        if (any_active != 0) {
+            const int idle_limit = (exhausted && in_cnt == 0) ? 32 * CHAINS + 1 : IKB_FABRIK_IDLE_T * CHAINS;
+            int n_idle = 0;
+#pragma unroll
+            for (int u = 0; u < CHAINS; ++u)
+                n_idle += 32 - __popc(active_mask[u]);
             bool leave = false;
             do {
-                bool more = false;
-                if (!zero_iter) {
-                    more = fabrik_pass(c, Tr, Tz, R0, Z0, d1, d2, start_band, goal_band);
-                    ++k;
-                }
-                const bool fin = active & (!more | (k >= max_iter));
-                const unsigned m = __ballot_sync(IKB_FULL_MASK, fin);
-                if (m != 0) {
-                    if (fin) {
-                        const int slot = (out_head + out_cnt + __popc(m & lt)) & (IKB_Q - 1);
-                        q.out_idx[slot] = idx;
-                        q.out_k[slot] = more ? (k | IKB_CAPPED_BIT) : k;
-                        q.out_c[0][slot] = c.r1; q.out_c[1][slot] = c.z1;
-                        q.out_c[2][slot] = c.r2; q.out_c[3][slot] = c.z2;
-                        active = false;
+                bool more[CHAINS], fin[CHAINS];
+                unsigned m[CHAINS], many = 0;
+#pragma unroll
+                for (int u = 0; u < CHAINS; ++u) {
+                    more[u] = false;
+                    if (!zero_iter) {
+                        more[u] = fabrik_pass(c[u], Tr[u], Tz[u], R0, Z0, d1, d2, start_band, goal_band);
+                        ++k[u];
                     }
-                    const int nf = __popc(m);
-                    out_cnt += nf;
-                    n_idle += nf;
-                    active_mask &= ~m;
-                    leave = (n_idle >= idle_limit) | (out_cnt >= 32) | (active_mask == 0);
+                }
+#pragma unroll
+                for (int u = 0; u < CHAINS; ++u) {
+                    fin[u] = active[u] & (!more[u] | (k[u] >= max_iter));
+                    m[u] = __ballot_sync(IKB_FULL_MASK, fin[u]);
+                    many |= m[u];
+                }
+                if (many != 0) {
+#pragma unroll
+                    for (int u = 0; u < CHAINS; ++u) {
+                        if (m[u] != 0) {
+                            if (fin[u]) {
+                                int slot = out_head + out_cnt + __popc(m[u] & lt);
+                                slot -= slot >= OUT_Q ? OUT_Q : 0;
+                                q.out_idx[slot] = idx[u];
+                                q.out_k[slot] = more[u] ? (k[u] | IKB_CAPPED_BIT) : k[u];
+                                q.out_c[0][slot] = c[u].r1; q.out_c[1][slot] = c[u].z1;
+                                q.out_c[2][slot] = c[u].r2; q.out_c[3][slot] = c[u].z2;
+                                active[u] = false;
+                            }
+                            const int nf = __popc(m[u]);
+                            out_cnt += nf;
+                            n_idle += nf;
+                            active_mask[u] &= ~m[u];
+                        }
+                    }
+                    any_active = 0;
+#pragma unroll
+                    for (int u = 0; u < CHAINS; ++u)
+                        any_active |= active_mask[u];
+                    // the parked-chain ring holds IKB_Q entries: leave as soon as one more pass could overflow it
+                    leave = (n_idle >= idle_limit) | (out_cnt >= 32) | (any_active == 0);
                 }
             } while (!leave);
             __syncwarp();
@@ -387,11 +432,12 @@ __global__ void __launch_bounds__(IKB_FABRIK_WARPS * 32, IKB_FABRIK_MIN_CTAS) fa
         // 4. the fp64 epilogue runs on a full warp of parked chains (or on the remainder once all
         //    work is done).  ONE call site: every row goes through the same instruction sequence,
         //    so results do not depend on where in the batch a target sits.
-        const bool drained = active_mask == 0 && exhausted && in_cnt == 0;
-        if (out_cnt >= 32 || (drained && out_cnt > 0)) {
+        const bool drained = any_active == 0 && exhausted && in_cnt == 0;
+        while (out_cnt >= 32 || (drained && out_cnt > 0)) {
             const int n_take = min(32, out_cnt);
             if (lane < n_take) {
-                const int slot = (out_head + lane) & (IKB_Q - 1);
+                int slot = out_head + lane;
+                slot -= slot >= OUT_Q ? OUT_Q : 0;
                 const int k_raw = q.out_k[slot], k_done = k_raw & (IKB_CAPPED_BIT - 1);
                 fabrik_epilogue(a, q.out_idx[slot], k_done, (double)q.out_c[0][slot], (double)q.out_c[1][slot],
                                 (double)q.out_c[2][slot], (double)q.out_c[3][slot]);
@@ -399,7 +445,8 @@ __global__ void __launch_bounds__(IKB_FABRIK_WARPS * 32, IKB_FABRIK_MIN_CTAS) fa
                 ++solved_local;
                 capped_local += (k_raw & IKB_CAPPED_BIT) ? 1u : 0u;
             }
-            out_head = (out_head + n_take) & (IKB_Q - 1);
+            out_head += n_take;
+            out_head -= out_head >= OUT_Q ? OUT_Q : 0;
             out_cnt -= n_take;
             __syncwarp();
         }
@@ -515,13 +562,13 @@ cudaError_t ikb_launch_fabrik_planar(const void *xyz, int xyz_f64, long long n, 
     // persistent grid: resident CTAs per SM x SM count, trimmed for small batches
     const int per_cta = IKB_FABRIK_WARPS * 32;
     long long want = (n + per_cta - 1) / per_cta;
-    long long grid = (long long)num_sms * 3;
+    long long grid = (long long)num_sms * (IKB_FABRIK_CHAINS == 1 ? IKB_FABRIK_MIN_CTAS : IKB_FABRIK_MIN_CTAS2);
     if (want < grid)
         grid = want;
     if (precision == IKB_FABRIK_F32)
-        fabrik_planar_kernel<float><<<(unsigned)grid, per_cta, 0, stream>>>(a);
+        fabrik_planar_kernel<float, IKB_FABRIK_CHAINS><<<(unsigned)grid, per_cta, 0, stream>>>(a);
     else
-        fabrik_planar_kernel<double><<<(unsigned)grid, per_cta, 0, stream>>>(a);
+        fabrik_planar_kernel<double, IKB_FABRIK_CHAINS><<<(unsigned)grid, per_cta, 0, stream>>>(a);
     return cudaGetLastError();
 }
 

@@ -11,37 +11,84 @@
 
 namespace {
 
-__device__ __forceinline__ void ikb_sincos(float x, float *s, float *c) { sincosf(x, s, c); }
+// sin/cos for |x| <= 2 pi (larger angles are rejected by the guard of forward.py:23-25 anyway):
+// two-term Cody-Waite reduction by pi/2 (|k| <= 4, exact products) + the cephes single-precision
+// kernels on [-pi/4, pi/4]; max error ~1.2e-7.  libdevice's sincosf carries a Payne-Hanek slow path whose
+// integer instructions made the fp32 FK kernel instruction-bound instead of HBM-bound.
+__device__ __forceinline__ void ikb_sincos(float x, float *s, float *c)
+{
+    const float k = rintf(x * 0.63661977236758134f);
+    float r = fmaf(k, -1.57079625129699707031f, x);
+    r = fmaf(k, -7.54978941586159635335e-8f, r);
+    const int q = (int)k;
+    const float r2 = r * r;
+    float sp = fmaf(r2, -1.9515295891e-4f, 8.3321608736e-3f);
+    sp = fmaf(sp, r2, -1.6666654611e-1f);
+    sp = fmaf(sp * r2, r, r);
+    float cp = fmaf(r2, 2.443315711809948e-5f, -1.388731625493765e-3f);
+    cp = fmaf(cp, r2, 4.166664568298827e-2f);
+    cp = fmaf(cp * r2, r2, fmaf(r2, -0.5f, 1.0f));
+    const float ss = (q & 1) ? cp : sp, cc = (q & 1) ? sp : cp;
+    *s = (q & 2) ? -ss : ss;
+    *c = ((q + 1) & 2) ? -cc : cc;
+}
 __device__ __forceinline__ void ikb_sincos(double x, double *s, double *c) { sincos(x, s, c); }
 
-// Position-only DH chain: p += R [a c, a s, eps]; R = R Rz(theta) Rx(alpha).
+// Position-only DH chain.  General form: p += R [a c, a s, eps]; R = R Rz(theta) Rx(alpha).
+// When joints 2..4 have alpha == 0 (rc.fk_planar_tail: every arm of the reference's family, robot.py:40) the
+// tail is planar in joint 1's frame and the product collapses to
+//   local = (sum a_i cos(phi_i), sum a_i sin(phi_i), sum eps_i),  phi_i = theta_2 + .. + theta_i
+//   p     = Rz(theta_1) ([a_1, 0, eps_1] + Rx(alpha_1) local)
+// with the cumulative angles formed by the addition theorems -- ~1/3 of the general path's instructions,
+// which is what lets the fp32 kernel run at HBM speed.
 template <typename Real>
 __device__ __forceinline__ bool fk_position(const IkbRobot &rc, const Real th[4], Real &px, Real &py,
                                             Real &pz)
 {
     const Real TWO_PI = (Real)6.283185307179586;
-    Real R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
-    px = py = pz = 0;
     bool ok = true;
+    Real s[4], c[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-        const Real t = th[i];
-        ok &= !(t < -TWO_PI) & !(t > TWO_PI);  // forward.py:23-25 (NaN passes, as upstream)
-        Real s, c;
-        ikb_sincos(t, &s, &c);
+        ok &= !(th[i] < -TWO_PI) & !(th[i] > TWO_PI);  // forward.py:23-25 (NaN passes, as upstream)
+        ikb_sincos(th[i], &s[i], &c[i]);
+    }
+    if (rc.fk_planar_tail) {
+        Real cs = c[1], sn = s[1];
+        Real u = (Real)rc.a[1] * cs, v = (Real)rc.a[1] * sn;
+#pragma unroll
+        for (int i = 2; i < 4; ++i) {
+            const Real cn = cs * c[i] - sn * s[i];
+            sn = sn * c[i] + cs * s[i];
+            cs = cn;
+            u += (Real)rc.a[i] * cs;
+            v += (Real)rc.a[i] * sn;
+        }
+        const Real w = (Real)(rc.eps[1] + rc.eps[2] + rc.eps[3]);
+        const Real ca = (Real)rc.cos_alpha[0], sa = (Real)rc.sin_alpha[0];
+        const Real lx = (Real)rc.a[0] + u, ly = v * ca - w * sa, lz = (Real)rc.eps[0] + v * sa + w * ca;
+        px = c[0] * lx - s[0] * ly;
+        py = s[0] * lx + c[0] * ly;
+        pz = lz;
+        return ok;
+    }
+    Real R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+    px = py = pz = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
         const Real a = (Real)rc.a[i], e = (Real)rc.eps[i];
-        const Real vx = a * c, vy = a * s;
+        const Real vx = a * c[i], vy = a * s[i];
         px += R[0] * vx + R[1] * vy + R[2] * e;
         py += R[3] * vx + R[4] * vy + R[5] * e;
         pz += R[6] * vx + R[7] * vy + R[8] * e;
         if (i < 3) {
             const Real ca = (Real)rc.cos_alpha[i], sa = (Real)rc.sin_alpha[i];
             // M = Rz(t) Rx(alpha) = [[c, -s ca, s sa], [s, c ca, -c sa], [0, sa, ca]]
-            const Real m01 = -s * ca, m02 = s * sa, m11 = c * ca, m12 = -c * sa;
+            const Real m01 = -s[i] * ca, m02 = s[i] * sa, m11 = c[i] * ca, m12 = -c[i] * sa;
 #pragma unroll
             for (int r = 0; r < 3; ++r) {
                 const Real r0 = R[3 * r], r1 = R[3 * r + 1], r2 = R[3 * r + 2];
-                R[3 * r] = r0 * c + r1 * s;
+                R[3 * r] = r0 * c[i] + r1 * s[i];
                 R[3 * r + 1] = r0 * m01 + r1 * m11 + r2 * sa;
                 R[3 * r + 2] = r0 * m02 + r1 * m12 + r2 * ca;
             }
@@ -63,6 +110,10 @@ struct FkArgs {
     IkbRobot rc;
 };
 
+// FK_ROWS rows per thread and loop trip, all of their loads issued before any arithmetic: at 28 B of
+// input per row the kernel needs ~5 MB in flight chip-wide to cover HBM latency.
+#define FK_ROWS 4
+
 template <typename Real>
 __global__ void __launch_bounds__(256) fk_kernel(const FkArgs a)
 {
@@ -73,47 +124,69 @@ __global__ void __launch_bounds__(256) fk_kernel(const FkArgs a)
 #pragma unroll
     for (int j = 0; j < 4; ++j)
         alpha_ok &= !(a.rc.alpha[j] < -6.283185307179586) & !(a.rc.alpha[j] > 6.283185307179586);
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += stride) {
-        Real th[4];
-        if (a.angles_f64) {
-            const double2 *p = reinterpret_cast<const double2 *>(a.angles) + 2 * i;
-            const double2 u = __ldg(p), v = __ldg(p + 1);
-            th[0] = (Real)u.x; th[1] = (Real)u.y; th[2] = (Real)v.x; th[3] = (Real)v.y;
-        } else {
-            const float4 u = __ldg(reinterpret_cast<const float4 *>(a.angles) + i);
-            th[0] = (Real)u.x; th[1] = (Real)u.y; th[2] = (Real)u.z; th[3] = (Real)u.w;
-        }
-        Real px, py, pz;
-        const bool ok = fk_position<Real>(a.rc, th, px, py, pz) & alpha_ok;
-        if (!ok) {
-            px = py = pz = (Real)__int_as_float(0x7fc00000);
-            atomicMin(&a.stats->first_fk_angle_range, a.index_base + i);
-        }
-        if (a.pos_out) {
-            if (a.angles_f64) {
-                double *o = reinterpret_cast<double *>(a.pos_out) + 3 * i;
-                o[0] = px; o[1] = py; o[2] = pz;
-            } else {
-                float *o = reinterpret_cast<float *>(a.pos_out) + 3 * i;
-                o[0] = (float)px; o[1] = (float)py; o[2] = (float)pz;
+    for (long long base = (long long)blockIdx.x * blockDim.x + threadIdx.x; base < a.n; base += stride * FK_ROWS) {
+        Real err_part = 0;  // per-trip partial sum in the working precision, folded into the fp64 total once
+        Real th[FK_ROWS][4];
+        Real tg[FK_ROWS][3];
+#pragma unroll
+        for (int u = 0; u < FK_ROWS; ++u) {
+            const long long i = base + u * stride;
+            if (i < a.n) {
+                if (a.angles_f64) {
+                    const double2 *p = reinterpret_cast<const double2 *>(a.angles) + 2 * i;
+                    const double2 v0 = __ldg(p), v1 = __ldg(p + 1);
+                    th[u][0] = (Real)v0.x; th[u][1] = (Real)v0.y; th[u][2] = (Real)v1.x; th[u][3] = (Real)v1.y;
+                } else {
+                    const float4 v = __ldg(reinterpret_cast<const float4 *>(a.angles) + i);
+                    th[u][0] = (Real)v.x; th[u][1] = (Real)v.y; th[u][2] = (Real)v.z; th[u][3] = (Real)v.w;
+                }
+                if (a.targets) {
+                    if (a.xyz_f64) {
+                        const double *p = reinterpret_cast<const double *>(a.targets) + 3 * i;
+                        tg[u][0] = (Real)__ldg(p); tg[u][1] = (Real)__ldg(p + 1); tg[u][2] = (Real)__ldg(p + 2);
+                    } else {  // no detour through double for fp32 buffers
+                        const float *p = reinterpret_cast<const float *>(a.targets) + 3 * i;
+                        tg[u][0] = (Real)__ldg(p); tg[u][1] = (Real)__ldg(p + 1); tg[u][2] = (Real)__ldg(p + 2);
+                    }
+                }
             }
         }
-        if (a.targets) {
-            double tx, ty, tz;
-            ikb_load_xyz(a.targets, a.xyz_f64, i, tx, ty, tz);
-            const Real dx = px - (Real)tx, dy = py - (Real)ty, dz = pz - (Real)tz;
-            const Real err = sqrt(dx * dx + dy * dy + dz * dz);
-            if (a.err_out) {
-                if (a.angles_f64)
-                    reinterpret_cast<double *>(a.err_out)[i] = err;
-                else
-                    reinterpret_cast<float *>(a.err_out)[i] = (float)err;
+#pragma unroll
+        for (int u = 0; u < FK_ROWS; ++u) {
+            const long long i = base + u * stride;
+            if (i >= a.n)
+                break;
+            Real px, py, pz;
+            const bool ok = fk_position<Real>(a.rc, th[u], px, py, pz) & alpha_ok;
+            if (!ok) {
+                px = py = pz = (Real)__int_as_float(0x7fc00000);
+                atomicMin(&a.stats->first_fk_angle_range, a.index_base + i);
             }
-            if (isfinite(err)) {
-                err_sum += (double)err;
-                ++err_cnt;
+            if (a.pos_out) {
+                if (a.angles_f64) {
+                    double *o = reinterpret_cast<double *>(a.pos_out) + 3 * i;
+                    o[0] = px; o[1] = py; o[2] = pz;
+                } else {
+                    float *o = reinterpret_cast<float *>(a.pos_out) + 3 * i;
+                    o[0] = (float)px; o[1] = (float)py; o[2] = (float)pz;
+                }
+            }
+            if (a.targets) {
+                const Real dx = px - tg[u][0], dy = py - tg[u][1], dz = pz - tg[u][2];
+                const Real err = sqrt(dx * dx + dy * dy + dz * dz);
+                if (a.err_out) {
+                    if (a.angles_f64)
+                        reinterpret_cast<double *>(a.err_out)[i] = err;
+                    else
+                        reinterpret_cast<float *>(a.err_out)[i] = (float)err;
+                }
+                if (isfinite(err)) {
+                    err_part += err;
+                    ++err_cnt;
+                }
             }
         }
+        err_sum += (double)err_part;
     }
     if (a.targets) {
         err_sum = ikb_warp_sum(err_sum);

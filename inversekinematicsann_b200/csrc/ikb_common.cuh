@@ -30,6 +30,7 @@ struct IkbRobot {
     int zero_iter;        // tol >= 1 or max_iter <= 0: the reference's while loop never runs
     // forward kinematics, reference forward.py:62-70: T_i = Rz(th_i) Tz(eps_i) Tx(a_i) Rx(alpha_i)
     double eps[4], a[4], cos_alpha[4], sin_alpha[4], alpha[4];
+    int fk_planar_tail;   // alpha[1..3] == 0: joints 2..4 rotate about parallel axes (closed-form FK)
 };
 
 // Device-side statistics block; host mirror is ikb_stats.  first_* start at IKB_I64_MAX.

@@ -61,6 +61,7 @@ def lib():
         L.iko_point_between_c.restype = ctypes.c_int
         L.iko_point_between_c.argtypes = [dp, dp, ctypes.c_double, ctypes.c_int, dp]
         L.iko_num_threads.restype = ctypes.c_int
+        L.iko_set_num_threads.argtypes = [ctypes.c_int]
         _LIB = L
     return _LIB
 
@@ -78,6 +79,10 @@ def _f64(a, shape=None):
     if shape is not None:
         a = a.reshape(shape)
     return a
+
+
+def set_num_threads(n: int) -> None:
+    lib().iko_set_num_threads(int(n))
 
 
 def num_threads() -> int:

@@ -56,3 +56,19 @@ def test_fk_error_of_fabrik_output_matches_oracle(golden_fabrik):
     pos, err, stats = get_engine().fk(ang, xyz)
     np.testing.assert_allclose(err, want, rtol=0, atol=1e-12)
     assert abs(stats.mean_fk_error - want.mean()) < 1e-12 and stats.n_fk_error == len(xyz)
+
+
+def test_general_dh_table_matches_oracle():
+    """A DH table with twists on every joint takes the general (non closed-form) chain path."""
+    from inversekinematicsann_b200.kinematics.forward import ForwardKinematics
+    from oracle import c_oracle
+    dh = [[0, np.pi / 2, 0, 0], [2, 0.5, -0.25, 0.1], [0.3, 2, 1.5, 2.5], [np.pi / 2, 0.3, -0.2, 0.1]]
+    rng = np.random.RandomState(4)
+    ang = rng.uniform(-np.pi, np.pi, size=(5000, 4))
+    st, want, _ = c_oracle.fk_positions(ang, dh=np.array(dh, dtype=np.float64))
+    fk = ForwardKinematics(dh)
+    np.testing.assert_allclose(fk.fkine_positions(ang), want, rtol=0, atol=1e-12)
+    np.testing.assert_allclose(fk.fkine_positions(ang.astype(np.float32)), want, rtol=0, atol=1e-5)
+    _, chain = fk.fkine(list(ang[0]))
+    _, want_chain = c_oracle.fk_chain(ang[0], dh=np.array(dh, dtype=np.float64))
+    np.testing.assert_allclose(np.array(chain), want_chain, rtol=0, atol=1e-12)
