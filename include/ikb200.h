@@ -149,6 +149,24 @@ int ikb_ann_solve_device(ikb_engine *e, const void *xyz, int xyz_dtype, int64_t 
 int ikb_ann_solve_host(ikb_engine *e, const void *xyz, int xyz_dtype, int64_t n,
                        float *angles_out, int mode, ikb_stats *stats);
 
+/* ---- trajectory generators (robot/position_generator.py:26-97), written straight into device memory ----
+ * kind / params (doubles):
+ *   IKB_GEN_CIRCLE      {radius, cx, cy, cz}                      circle(radius, n, centre)            :26-31
+ *   IKB_GEN_SPRING      {len_x, len_y, len_z, n_total}            spring(n_total, len_x, len_y, len_z) :72-78
+ *   IKB_GEN_CUBE        {step, len_x, len_y, len_z, sx, sy, sz, nx, ny}   cube(step, ...), nx = len(arange(0, len_x, step)) :39-46
+ *   IKB_GEN_CUBE_RANDOM {len_x, len_y, len_z, sx, sy, sz}         cube_random: start + len * U[0,1)    :48-55
+ *   IKB_GEN_NORMAL      {xlo, xhi, ylo, yhi, zlo, zhi, std_dev}   random_distribution(.., 'normal', std_dev) :80-97
+ * Rows [row_offset, row_offset + n) of the trajectory are produced (a shard generates only its own range).
+ * The random kinds use Philox4x32-10 keyed by (seed, row): same distributions as the reference's numpy / scipy
+ * calls, reproducible per seed, but not numpy's Mersenne-Twister stream. */
+#define IKB_GEN_CIRCLE 0
+#define IKB_GEN_SPRING 1
+#define IKB_GEN_CUBE 2
+#define IKB_GEN_CUBE_RANDOM 3
+#define IKB_GEN_NORMAL 4
+int ikb_generate_device(ikb_engine *e, int kind, const double *params, int n_params, int64_t n, int64_t row_offset,
+                        void *xyz_out, int xyz_dtype, uint64_t seed, void *stream);
+
 /* ---- measurement helpers --------------------------------------------------------------------- */
 /* dependent-FMA-chain microbenchmark on `stream`'s device: achieved TFLOP/s (2 flops per FMA) of
  * the fp32 (dtype IKB_F32) or fp64 (IKB_F64) CUDA-core pipe; the roofline denominator for FABRIK. */

@@ -23,7 +23,7 @@ EXPORTED_SYMBOLS = [
     "ikb_fabrik_solve_device", "ikb_fabrik_solve_host", "ikb_fabrik_calculate_host",
     "ikb_fk_device", "ikb_fk_host", "ikb_fk_chain_host",
     "ikb_mlp_load", "ikb_ann_solve_device", "ikb_ann_solve_host",
-    "ikb_microbench_fma", "ikb_launch_count",
+    "ikb_generate_device", "ikb_microbench_fma", "ikb_launch_count",
 ]
 
 
@@ -84,6 +84,7 @@ def load():
                                ctypes.POINTER(vp), ctypes.POINTER(vp), vp, vp, vp, vp]),
         "ikb_ann_solve_device": (i32, [engine, vp, i32, i64, vp, i32, vp]),
         "ikb_ann_solve_host": (i32, [engine, vp, i32, i64, vp, i32, stats_p]),
+        "ikb_generate_device": (i32, [engine, i32, vp, i32, i64, i64, vp, i32, ctypes.c_uint64, vp]),
         "ikb_microbench_fma": (i32, [engine, i32, ctypes.POINTER(dbl)]),
         "ikb_launch_count": (i64, [engine]),
     }

@@ -28,6 +28,8 @@ cudaError_t ikb_launch_check_limits(const void *xyz, int xyz_f64, long long n, l
                                     IkbDeviceStats *stats, const IkbRobot &rc, int num_sms,
                                     cudaStream_t stream);
 cudaError_t ikb_launch_fma_peak(int f64, void *sink, int iters, int num_sms, cudaStream_t stream);
+cudaError_t ikb_launch_generate(int kind, const double *params, int n_params, long long n, long long row_offset,
+                                void *out, int out_f64, unsigned long long seed, int num_sms, cudaStream_t stream);
 
 namespace {
 
@@ -561,6 +563,20 @@ int ikb_ann_solve_host(ikb_engine *e, const void *xyz, int xyz_dtype, int64_t n,
         IKB_CUDA(e, cudaMemcpyAsync((char *)angles_out + lo * out_row, s.d_out, m * out_row, cudaMemcpyDeviceToHost, s.stream));
     }
     return host_end(e, stats);
+}
+
+// ---- trajectory generators ------------------------------------------------------------------------
+int ikb_generate_device(ikb_engine *e, int kind, const double *params, int n_params, int64_t n, int64_t row_offset,
+                        void *xyz_out, int xyz_dtype, uint64_t seed, void *stream)
+{
+    if (!e || n < 0 || (n > 0 && !xyz_out) || bad_dtype(xyz_dtype) || kind < 0 || kind > 4 || n_params < 0 ||
+        n_params > 12 || (n_params > 0 && !params))
+        return fail(e, IKB_ERR_INVALID, "ikb_generate_device: bad argument");
+    IKB_CUDA(e, cudaSetDevice(e->device));
+    IKB_CUDA(e, ikb_launch_generate(kind, params, n_params, n, row_offset, xyz_out, xyz_dtype == IKB_F64, seed,
+                                    e->num_sms, (cudaStream_t)stream));
+    e->launches += (n > 0);
+    return IKB_OK;
 }
 
 // ---- measurement ----------------------------------------------------------------------------------
