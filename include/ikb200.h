@@ -51,6 +51,7 @@ extern "C" {
 /* MLP arithmetic mode */
 #define IKB_MLP_FP32_SIMT 0 /* fp32 FFMA on the CUDA cores (Keras-fp32 grade)                    */
 #define IKB_MLP_FP16X3_TC 1 /* tcgen05 kind::f16, 3-term hi/lo split, fp32 accumulate in TMEM    */
+#define IKB_MLP_FP16X3_TS 2 /* same arithmetic, activations as the A operand in TMEM (TS-mode MMA) */
 
 typedef struct ikb_engine ikb_engine;
 

@@ -13,7 +13,7 @@ IKB_OK = 0
 IKB_ERR_INVALID, IKB_ERR_CUDA, IKB_ERR_NO_MODEL, IKB_ERR_UNSUPPORTED = -1, -2, -3, -4
 IKB_F32, IKB_F64 = 0, 1
 IKB_FABRIK_F64, IKB_FABRIK_F32 = 0, 1
-IKB_MLP_FP32_SIMT, IKB_MLP_FP16X3_TC = 0, 1
+IKB_MLP_FP32_SIMT, IKB_MLP_FP16X3_TC, IKB_MLP_FP16X3_TS = 0, 1, 2
 
 # every symbol include/ikb200.h declares (tests check that the built library exports them all)
 EXPORTED_SYMBOLS = [

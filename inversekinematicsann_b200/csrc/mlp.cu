@@ -219,6 +219,8 @@ void ikb_mlp_free(IkbMlp &m)
     m.loaded = false;
     ikb_mlp_tc_delete(m.tc);
     m.tc = nullptr;
+    ikb_mlp_tc2_delete(m.tc2);
+    m.tc2 = nullptr;
 }
 
 int ikb_mlp_upload(IkbMlp &m, int n_layers, const int *dims, const float *const *weights,
@@ -295,6 +297,12 @@ int ikb_mlp_upload(IkbMlp &m, int n_layers, const int *dims, const float *const 
         if (rc != IKB_OK)
             return rc;
     }
+    m.tc2 = ikb_mlp_tc2_new();
+    {
+        const int rc = ikb_mlp_tc2_pack(*m.tc2, n_layers, dims, weights, biases, mean_x, scale_x, mean_y, scale_y, err);
+        if (rc != IKB_OK)
+            return rc;
+    }
     m.dev = d;
     m.arena_bytes = total;
     m.macs_per_row = macs;
@@ -321,6 +329,12 @@ int ikb_mlp_launch(const IkbMlp &m, const void *xyz, int xyz_f64, long long n, l
     if (mode == IKB_MLP_FP16X3_TC) {
         const int rc_tc = ikb_mlp_tc_launch(*m.tc, xyz, xyz_f64, n, index_base, angles_out, stats, rc, num_sms,
                                             stream, err);
+        launches = rc_tc == IKB_OK ? 1 : 0;
+        return rc_tc;
+    }
+    if (mode == IKB_MLP_FP16X3_TS) {
+        const int rc_tc = ikb_mlp_tc2_launch(*m.tc2, xyz, xyz_f64, n, index_base, angles_out, stats, rc, num_sms,
+                                             stream, err);
         launches = rc_tc == IKB_OK ? 1 : 0;
         return rc_tc;
     }

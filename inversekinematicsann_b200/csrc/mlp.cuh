@@ -30,9 +30,20 @@ int ikb_mlp_tc_launch(const IkbMlpTc &t, const void *xyz, int xyz_f64, long long
                       float *angles_out, IkbDeviceStats *stats, const IkbRobot &rc, int num_sms,
                       cudaStream_t stream, std::string &err);
 
+struct IkbMlpTc2;  // second tensor-core layout: activations as a TMEM A operand (mlp_tc2.cu)
+IkbMlpTc2 *ikb_mlp_tc2_new();
+void ikb_mlp_tc2_delete(IkbMlpTc2 *t);
+int ikb_mlp_tc2_pack(IkbMlpTc2 &t, int n_layers, const int *dims, const float *const *weights,
+                     const float *const *biases, const double mean_x[3], const double scale_x[3],
+                     const double mean_y[4], const double scale_y[4], std::string &err);
+int ikb_mlp_tc2_launch(const IkbMlpTc2 &t, const void *xyz, int xyz_f64, long long n, long long index_base,
+                       float *angles_out, IkbDeviceStats *stats, const IkbRobot &rc, int num_sms,
+                       cudaStream_t stream, std::string &err);
+
 struct IkbMlp {
     bool loaded = false;
     IkbMlpTc *tc = nullptr;
+    IkbMlpTc2 *tc2 = nullptr;
     IkbMlpDevice dev;
     void *arena = nullptr;  // one device allocation holding all padded weights and biases
     size_t arena_bytes = 0;

@@ -155,9 +155,10 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 // tanh(x) = sign(x) (1 - e) / (1 + e), e = 2^(-2 |x| log2 e): two MUFU ops, absolute error ~1e-7
 __device__ __forceinline__ float fast_tanh(float x)
 {
-    const float e = exp2f(-2.8853900817779268f * fabsf(x));
-    const float t = __fdividef(1.0f - e, 1.0f + e);
-    return copysignf(t, x);
+    float e, r;  // exactly two MUFU ops, no range fix-ups: e in (0, 1], 1 + e in (1, 2]
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-2.8853900817779268f * fabsf(x)));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+    return copysignf((1.0f - e) * r, x);
 }
 
 // byte offset of element (row, k) inside a [rows x 64] fp16 K-major tile with the 128-byte swizzle
@@ -381,9 +382,12 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_tc_kernel(const TcArgs a)
                         for (int r = 0; r < 32; ++r) {
                             const float acc = fmaf(__uint_as_float(dl[r]), LO_UNSCALE, __uint_as_float(dh[r]));
                             const float y = fast_tanh(fmaf(acc, inv_sw, b));
-                            const __half hi = __float2half_rn(y);
-                            const __half lo = __float2half_rn((y - __half2float(hi)) * LO_SCALE);
-                            packed[ft][r] = (uint32_t)__half_as_ushort(hi) | ((uint32_t)__half_as_ushort(lo) << 16);
+                            // one full-rate cvt.rn.f16x2.f32 per split instead of two quarter-rate scalar F2Fs:
+                            // first (y, 0) -> hi, then ((y - hi) 2^11, hi) -> packed {lo | hi}
+                            const __half2 h2 = __floats2half2_rn(y, 0.0f);
+                            const float hif = __low2float(h2);
+                            const __half2 p2 = __floats2half2_rn(hif, (y - hif) * LO_SCALE);  // .x = hi (exact), .y = lo
+                            packed[ft][r] = *reinterpret_cast<const uint32_t *>(&p2);
                         }
                         // pairs 0 .. NT-2 die while the last feature tile is being multiplied: flush them in order
                         // once the second-to-last tile has been computed, the last one right after its own compute

@@ -1,0 +1,682 @@
+// mlp_tc2.cu -- K2, second tensor-core layout (IKB_MLP_FP16X3_TS): activations as the A operand in TMEM.
+//
+// mlp_tc.cu is bound by shared-memory bandwidth: with 64 rows per CTA, streaming 1 MB of weights per layer
+// through smem (TMA write + MMA read) and re-reading the activation granules for every feature tile costs
+// 2.9 MB of smem traffic per layer.  This layout halves the traffic per row:
+//   * 128 REAL batch rows per CTA = UMMA M = 128 = TMEM lanes, so every (row, feature) sum lives in one lane;
+//   * x_hi (fp16) lives in TMEM (256 columns, two k per 32-bit column) and feeds the MMA as a TMEM A operand
+//     (TS mode, no smem reads at all); only x_lo (fp16) stays in shared memory (128 KB, K-major, 128B swizzle);
+//   * weights are the B operand, N = 256 features per UMMA, tiles of 256 features x 64 k (32 KB) pre-swizzled
+//     on the host and streamed by the TMA engine through a 3-stage ring;
+//   * three products per k step: x_hi w_hi (TS), x_lo w_hi (SS), x_hi w_lo (TS), all into ONE fp32 accumulator
+//     D[128 lanes x 256 columns] per N half.  x is stored times 2^6 so that x_lo stays a normal fp16 number while
+//     sharing the accumulator with x_hi; the factor is folded into the per-layer output scale.
+// TMEM: columns [0, 256) = x_hi, [256, 512) = D.  Per layer: MMA(half 0) -> epilogue drains D into registers ->
+// MMA(half 1) runs while the epilogue turns half 0 into the next layer's activations (kept packed in registers
+// until the issuer's tcgen05.commit says the old activations are dead) -> store (tcgen05.st for x_hi, st.shared
+// for x_lo) -> the next layer starts on the k range that is already there while half 1 is still being converted.
+// The 3-input first layer and the 4-output last layer run on the CUDA cores of the epilogue warps.
+#include <cuda_fp16.h>
+
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+#include "mlp.cuh"
+
+#ifdef IKB_TC_DEBUG
+__device__ unsigned long long g_tc2_dbg[16];
+#define DBG_T0() const long long _t0 = clock64()
+#define DBG_ADD(i) do { if (blockIdx.x == 0) g_tc2_dbg[i] += (unsigned long long)(clock64() - _t0); } while (0)
+#else
+#define DBG_T0() do {} while (0)
+#define DBG_ADD(i) do {} while (0)
+#endif
+
+namespace {
+
+constexpr int ROWS = 128;             // targets per CTA tile = UMMA M
+constexpr int GRAN_BYTES = 16384;     // x_lo granule: 128 rows x 64 k x fp16
+constexpr int WTILE_BYTES = 32768;    // weight tile: up to 256 features x 64 k x fp16
+constexpr int W_STAGES = 3;
+constexpr int N_EPI_WARPS = 8;
+constexpr int THREADS = (2 + N_EPI_WARPS) * 32;
+constexpr float X_SCALE = 64.0f;      // activations are stored times 2^6
+constexpr int TMEM_A_COL = 0, TMEM_D_COL = 256;
+
+struct Tc2Net {
+    int n_mma_layers;        // hidden layers 2..NH
+    int hp;                  // common padded hidden width (multiple of 128, <= 512)
+    const __half *w_tiles;   // [layer][n half][k chunk][hi|lo] tiles of WTILE_BYTES (rows beyond the half's width unused)
+    const float *w_first;    // [3][hp]
+    const float *b_hidden;   // [1 + n_mma_layers][hp]
+    const float *out_scale;  // [n_mma_layers]  1 / (weight scale * X_SCALE)
+    const float *w_last;     // [hp][4]
+    float b_last[4];
+    double mean_x[3], scale_x[3];
+    float mean_y[4], scale_y[4];
+};
+
+struct Tc2Args {
+    const void *xyz;
+    int xyz_f64;
+    long long n;
+    long long index_base;
+    float *out;
+    IkbDeviceStats *stats;
+    IkbRobot rc;
+    Tc2Net net;
+};
+
+// ---- PTX helpers (same conventions as mlp_tc.cu) --------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "TS_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra TS_DONE;\n"
+        "bra TS_WAIT;\n"
+        "TS_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr)  // K-major, 128B swizzle, 8-row groups 1024 B apart
+{
+    return (uint64_t)((smem_addr >> 4) & 0x3FFF) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+// D[tmem] (+)= A[smem] * B[smem]
+__device__ __forceinline__ void umma_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc)
+{
+    asm volatile(
+        "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc)
+        : "memory");
+}
+// D[tmem] (+)= A[tmem] * B[smem]
+__device__ __forceinline__ void umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t acc)
+{
+    asm volatile(
+        "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n}\n" ::"r"(d_tmem),
+        "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(acc)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t *bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32])
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// tanh(x) = sign(x) (1 - e) / (1 + e), e = 2^(-2 |x| log2 e): exactly two MUFU ops (ex2, rcp) and no range
+// fix-ups (e is in (0, 1], 1 + e in (1, 2]); absolute error ~1e-7
+__device__ __forceinline__ float fast_tanh(float x)
+{
+    float e, r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-2.8853900817779268f * fabsf(x)));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+    return copysignf((1.0f - e) * r, x);
+}
+
+__device__ __host__ __forceinline__ int swz_off(int row, int k)  // [rows x 64] fp16 K-major tile, 128B swizzle
+{
+    return row * 128 + ((((k >> 3) ^ (row & 7)) & 7) << 4) + ((k & 7) << 1);
+}
+
+// y -> (hi, lo) fp16 split of X_SCALE * y, two consecutive features packed per 32-bit word (even feature low)
+__device__ __forceinline__ void split_pair(float y0, float y1, uint32_t &hi, uint32_t &lo)
+{
+    // cvt.rn.f16x2.f32 converts and packs two floats in one full-rate instruction (the scalar F2F.F16.F32
+    // shares the quarter-rate pipe with MUFU and made the epilogue, not the MMA, the bottleneck)
+    const float s0 = y0 * X_SCALE, s1 = y1 * X_SCALE;
+    const __half2 h = __floats2half2_rn(s0, s1);
+    const float2 hf = __half22float2(h);
+    const __half2 l = __floats2half2_rn(s0 - hf.x, s1 - hf.y);
+    hi = *reinterpret_cast<const uint32_t *>(&h);
+    lo = *reinterpret_cast<const uint32_t *>(&l);
+}
+
+// Everything an epilogue thread needs to turn pre-activations into the next layer's operands.
+struct EpiCtx {
+    const Tc2Net *net;
+    unsigned char *xlo;
+    uint64_t *a_free, *act_ready;
+    uint32_t tmem_base, lane_base;
+    int row, lane, HP;
+    float in0, in1, in2;   // scaled inputs of this thread's row (first layer)
+};
+
+// One N half of one layer for one thread: `ncols` (64 or 128) features starting at f0.
+// FIRST: pre-activations come from the 3 inputs (layer 1, CUDA cores, libm tanhf); otherwise from the fp32
+// accumulators `d` (already in registers).  Results are packed IN PLACE over `d` (word 2t = the x_hi pair of
+// features 2t, 2t+1 of that group of 32, word 2t+1 = the x_lo pair), so no second register array is needed;
+// they become the next layer's x_hi (TMEM) / x_lo (smem), or, for the last hidden layer, go straight into the 4
+// output sums (the output layer needs fp32 activations anyway).
+// Layer 1 (3 -> HP) for one thread and one N half: a rolled loop over chunks of 8 features, stored at once
+// (nothing reads the activation buffers while a tile's first layer runs), or fed to the output sums when the
+// network has a single hidden layer.
+__device__ __forceinline__ void first_layer_half(const EpiCtx &cx, int f0, int ncols, bool last_hidden, int ready_idx,
+                                                 float (&out_acc)[4])
+{
+    const Tc2Net &net = *cx.net;
+    const uint32_t a_addr = cx.tmem_base + cx.lane_base + TMEM_A_COL + (f0 >> 1);
+    tc_fence_after();
+#pragma unroll 1
+    for (int c = 0; c < ncols; c += 8) {
+        uint32_t hi[4], lo[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            float y[2];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const int f = f0 + c + 2 * t + u;
+                y[u] = tanhf(fmaf(cx.in2, __ldg(net.w_first + 2 * cx.HP + f),
+                                  fmaf(cx.in1, __ldg(net.w_first + cx.HP + f),
+                                       fmaf(cx.in0, __ldg(net.w_first + f), __ldg(net.b_hidden + f)))));
+                if (last_hidden) {
+                    const float4 w = __ldg(reinterpret_cast<const float4 *>(net.w_last) + f);
+                    out_acc[0] = fmaf(y[u], w.x, out_acc[0]); out_acc[1] = fmaf(y[u], w.y, out_acc[1]);
+                    out_acc[2] = fmaf(y[u], w.z, out_acc[2]); out_acc[3] = fmaf(y[u], w.w, out_acc[3]);
+                }
+            }
+            split_pair(y[0], y[1], hi[t], lo[t]);
+        }
+        if (!last_hidden) {
+            asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a_addr + (c >> 1)), "r"(hi[0]),
+                         "r"(hi[1]), "r"(hi[2]), "r"(hi[3])
+                         : "memory");
+            const int f = f0 + c;
+            unsigned char *dst = cx.xlo + (size_t)(f >> 6) * GRAN_BYTES + cx.row * 128 +
+                                 (((((f & 63) >> 3) ^ (cx.row & 7)) & 7) << 4);
+            *reinterpret_cast<uint4 *>(dst) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        }
+    }
+    if (last_hidden)
+        return;
+    tmem_st_wait();
+    fence_proxy_async();
+    tc_fence_before();
+    __syncwarp();
+    if (cx.lane == 0)
+        mbar_arrive(&cx.act_ready[ready_idx]);
+}
+
+template <bool FIRST>
+__device__ __forceinline__ void finish_half(const EpiCtx &cx, uint32_t (&d)[4][32], int f0, int ncols,
+                                            bool last_hidden, bool wait_free, uint32_t free_parity, int ready_idx,
+                                            float oscale, const float *bias, float (&out_acc)[4])
+{
+    const Tc2Net &net = *cx.net;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        if (q * 32 < ncols) {
+#pragma unroll
+            for (int t = 0; t < 16; ++t) {
+                const int f = f0 + q * 32 + 2 * t;
+                float y0, y1;
+                if (FIRST) {
+                    y0 = tanhf(fmaf(cx.in2, __ldg(net.w_first + 2 * cx.HP + f),
+                                    fmaf(cx.in1, __ldg(net.w_first + cx.HP + f),
+                                         fmaf(cx.in0, __ldg(net.w_first + f), __ldg(net.b_hidden + f)))));
+                    y1 = tanhf(fmaf(cx.in2, __ldg(net.w_first + 2 * cx.HP + f + 1),
+                                    fmaf(cx.in1, __ldg(net.w_first + cx.HP + f + 1),
+                                         fmaf(cx.in0, __ldg(net.w_first + f + 1), __ldg(net.b_hidden + f + 1)))));
+                } else {
+                    y0 = fast_tanh(fmaf(__uint_as_float(d[q][2 * t]), oscale, __ldg(bias + f)));
+                    y1 = fast_tanh(fmaf(__uint_as_float(d[q][2 * t + 1]), oscale, __ldg(bias + f + 1)));
+                }
+                if (last_hidden) {
+                    const float4 w0 = __ldg(reinterpret_cast<const float4 *>(net.w_last) + f);
+                    const float4 w1 = __ldg(reinterpret_cast<const float4 *>(net.w_last) + f + 1);
+                    out_acc[0] = fmaf(y1, w1.x, fmaf(y0, w0.x, out_acc[0]));
+                    out_acc[1] = fmaf(y1, w1.y, fmaf(y0, w0.y, out_acc[1]));
+                    out_acc[2] = fmaf(y1, w1.z, fmaf(y0, w0.z, out_acc[2]));
+                    out_acc[3] = fmaf(y1, w1.w, fmaf(y0, w0.w, out_acc[3]));
+                } else {
+                    split_pair(y0, y1, d[q][2 * t], d[q][2 * t + 1]);
+                }
+            }
+        }
+    }
+    if (last_hidden)
+        return;
+    if (wait_free) {
+        DBG_T0();
+        mbar_wait(cx.a_free, free_parity);  // the MMAs of this layer no longer read x_hi / x_lo
+        if (threadIdx.x == 64) DBG_ADD(5);
+    }
+    tc_fence_after();
+    const uint32_t a_addr = cx.tmem_base + cx.lane_base + TMEM_A_COL + (f0 >> 1);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        if (q * 32 < ncols) {
+            // x_hi pairs of this group -> 16 TMEM columns
+            asm volatile(
+                "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, "
+                "%15, %16};" ::"r"(a_addr + q * 16),
+                "r"(d[q][0]), "r"(d[q][2]), "r"(d[q][4]), "r"(d[q][6]), "r"(d[q][8]), "r"(d[q][10]), "r"(d[q][12]),
+                "r"(d[q][14]), "r"(d[q][16]), "r"(d[q][18]), "r"(d[q][20]), "r"(d[q][22]), "r"(d[q][24]), "r"(d[q][26]),
+                "r"(d[q][28]), "r"(d[q][30])
+                : "memory");
+            // x_lo pairs -> shared memory, 16-byte chunks of 8 features, swizzled K-major rows
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const int f = f0 + q * 32 + c * 8;
+                unsigned char *dst = cx.xlo + (size_t)(f >> 6) * GRAN_BYTES + cx.row * 128 +
+                                     (((((f & 63) >> 3) ^ (cx.row & 7)) & 7) << 4);
+                *reinterpret_cast<uint4 *>(dst) =
+                    make_uint4(d[q][8 * c + 1], d[q][8 * c + 3], d[q][8 * c + 5], d[q][8 * c + 7]);
+            }
+        }
+    }
+    tmem_st_wait();
+    fence_proxy_async();
+    tc_fence_before();
+    __syncwarp();
+    if (cx.lane == 0)
+        mbar_arrive(&cx.act_ready[ready_idx]);
+}
+
+__global__ void __launch_bounds__(THREADS, 1) mlp_tc2_kernel(const Tc2Args a)
+{
+    extern __shared__ __align__(1024) unsigned char smem[];
+    const Tc2Net &net = a.net;
+    const int HP = net.hp, KG = HP >> 6, NHALF = (HP + 255) >> 8, NM = net.n_mma_layers;
+    unsigned char *xlo = smem;                                     // KG granules of x_lo
+    unsigned char *wring = smem + (size_t)KG * GRAN_BYTES;          // W_STAGES weight tiles
+    float *s_io = reinterpret_cast<float *>(wring + (size_t)W_STAGES * WTILE_BYTES);  // [128][4] inputs / output partials
+    uint64_t *bars = reinterpret_cast<uint64_t *>(s_io + ROWS * 4);
+    uint64_t *w_full = bars, *w_empty = bars + W_STAGES;
+    uint64_t *d_full = w_empty + W_STAGES, *d_empty = d_full + 1;   // the single accumulator: MMA <-> epilogue
+    uint64_t *act_ready = d_empty + 1;                              // [2] epilogue -> MMA: k half of the next input stored
+    uint64_t *a_free = act_ready + 2;                               // MMA -> epilogue: this layer's input is dead
+    uint32_t *s_tmem = reinterpret_cast<uint32_t *>(a_free + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < W_STAGES; ++i) {
+            mbar_init(&w_full[i], 1);
+            mbar_init(&w_empty[i], 1);
+        }
+        mbar_init(d_full, 1);
+        mbar_init(d_empty, N_EPI_WARPS);
+        mbar_init(&act_ready[0], N_EPI_WARPS);
+        mbar_init(&act_ready[1], N_EPI_WARPS);
+        mbar_init(a_free, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "r"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *s_tmem;
+    const long long n_tiles = (a.n + ROWS - 1) / ROWS;
+
+    if (warp == 0) {
+        // ===== TMA producer: per layer and N half, for every k chunk the w_hi tile then the w_lo tile =====
+        if (lane == 0) {
+            int s = 0;
+            uint32_t ph = 1;
+            const size_t tiles_per_net = (size_t)NM * NHALF * KG * 2;
+            for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                const unsigned char *src = reinterpret_cast<const unsigned char *>(net.w_tiles);
+                for (size_t t = 0; t < tiles_per_net; ++t, src += WTILE_BYTES) {
+                    const int nh = (int)((t / (2 * (size_t)KG)) % NHALF);
+                    const uint32_t bytes = (uint32_t)min(256, HP - 256 * nh) * 128u;
+                    mbar_wait(&w_empty[s], ph);
+                    mbar_expect_tx(&w_full[s], bytes);
+                    tma_load_1d(wring + (size_t)s * WTILE_BYTES, src, bytes, &w_full[s]);
+                    if (++s == W_STAGES) {
+                        s = 0;
+                        ph ^= 1;
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            const uint64_t b_desc_base = make_desc(smem_u32(wring));
+            const uint64_t xlo_desc_base = make_desc(smem_u32(xlo));
+            constexpr uint32_t GRAN_DESC = GRAN_BYTES >> 4, WTILE_DESC = WTILE_BYTES >> 4;
+            const uint32_t d_tmem = tmem_base + TMEM_D_COL, a_tmem = tmem_base + TMEM_A_COL;
+            int s = 0;
+            uint32_t ph = 0, use = 0, duse = 0;  // use: MMA layers issued so far, duse: accumulator uses so far
+#ifdef IKB_TC_DEBUG
+            const long long _tstart = clock64();
+#endif
+            for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                for (int m = 0; m < NM; ++m, ++use) {
+                    for (int nh = 0; nh < NHALF; ++nh, ++duse) {
+                        const uint32_t nfeat = (uint32_t)min(256, HP - 256 * nh);
+                        // D fp32, A/B fp16, K-major, N = features of this half, M = 128
+                        const uint32_t idesc = (1u << 4) | ((nfeat >> 3) << 17) | ((128u >> 4) << 24);
+                        { DBG_T0(); mbar_wait(d_empty, (duse & 1) ^ 1); DBG_ADD(3); }  // the epilogue has drained the accumulator
+                        tc_fence_after();
+                        for (int kc = 0; kc < KG; ++kc) {
+                            if (nh == 0 && (kc & 3) == 0) {  // k half kc/4 of this layer's input has been stored
+                                { DBG_T0(); mbar_wait(&act_ready[kc >> 2], use & 1); DBG_ADD(2); }
+                                tc_fence_after();
+                            }
+                            const uint32_t a_cols = a_tmem + kc * 32;  // 64 k = 32 columns of packed fp16 pairs
+                            const uint64_t xlo_desc = xlo_desc_base + (uint64_t)(kc * GRAN_DESC);
+                            // w_hi tile: x_hi (TMEM) and x_lo (smem) both multiply it
+                            { DBG_T0(); mbar_wait(&w_full[s], ph); DBG_ADD(1); }
+                            tc_fence_after();
+                            uint64_t b_desc = b_desc_base + (uint64_t)(s * WTILE_DESC);
+#pragma unroll
+                            for (int ks = 0; ks < 4; ++ks)
+                                umma_ts(d_tmem, a_cols + ks * 8, b_desc + 2 * ks, idesc, (kc | ks) != 0);
+#pragma unroll
+                            for (int ks = 0; ks < 4; ++ks)
+                                umma_ss(d_tmem, xlo_desc + 2 * ks, b_desc + 2 * ks, idesc, 1);
+                            umma_commit(&w_empty[s]);
+                            if (++s == W_STAGES) { s = 0; ph ^= 1; }
+                            // w_lo tile: only x_hi multiplies it (x_lo w_lo is below fp32 resolution)
+                            { DBG_T0(); mbar_wait(&w_full[s], ph); DBG_ADD(1); }
+                            tc_fence_after();
+                            b_desc = b_desc_base + (uint64_t)(s * WTILE_DESC);
+#pragma unroll
+                            for (int ks = 0; ks < 4; ++ks)
+                                umma_ts(d_tmem, a_cols + ks * 8, b_desc + 2 * ks, idesc, 1);
+                            umma_commit(&w_empty[s]);
+                            if (++s == W_STAGES) { s = 0; ph ^= 1; }
+                        }
+                        umma_commit(d_full);
+                    }
+                    umma_commit(a_free);  // every read of this layer's x_hi / x_lo has completed
+                }
+            }
+#ifdef IKB_TC_DEBUG
+            if (blockIdx.x == 0) g_tc2_dbg[0] += (unsigned long long)(clock64() - _tstart);
+#endif
+        }
+    } else {
+        // ===== epilogue warps: thread = (batch row = TMEM lane, half of the columns of the N half) =====
+        const int ew = warp - 2;
+        const int sub = warp & 3;             // TMEM sub-partition this warp may access
+        const int ch = ew >> 2;               // column half
+        const int row = sub * 32 + lane;      // batch row within the tile
+        const int et = ew * 32 + lane;
+        const uint32_t lane_base = (uint32_t)(sub * 32) << 16;
+        uint32_t use = 0, duse = 0;
+        for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            const long long row0 = tile * ROWS;
+            // ---- inputs: x_scaler.transform in fp64 -> fp32 (ann.py:72), workspace limits (inverse.py:154) ----
+            if (et < ROWS) {
+                const long long i = row0 + et;
+                float v0 = 0.f, v1 = 0.f, v2 = 0.f;
+                if (i < a.n) {
+                    double x, y, z;
+                    ikb_load_xyz(a.xyz, a.xyz_f64, i, x, y, z);
+                    if (ikb_out_of_limits(a.rc, x, y, z))
+                        atomicMin(&a.stats->first_out_of_limits, a.index_base + i);
+                    v0 = (float)((x - net.mean_x[0]) / net.scale_x[0]);
+                    v1 = (float)((y - net.mean_x[1]) / net.scale_x[1]);
+                    v2 = (float)((z - net.mean_x[2]) / net.scale_x[2]);
+                }
+                s_io[et * 4 + 0] = v0; s_io[et * 4 + 1] = v1; s_io[et * 4 + 2] = v2;
+            }
+            asm volatile("bar.sync 1, %0;" ::"n"(N_EPI_WARPS * 32));
+            const float in0 = s_io[row * 4], in1 = s_io[row * 4 + 1], in2 = s_io[row * 4 + 2];
+            float out_acc[4] = {0.f, 0.f, 0.f, 0.f};  // output layer partial sums of this thread's features
+
+            EpiCtx cx;
+            cx.net = &net; cx.xlo = xlo; cx.a_free = a_free; cx.act_ready = act_ready; cx.tmem_base = tmem_base;
+            cx.lane_base = lane_base; cx.row = row; cx.lane = lane; cx.HP = HP; cx.in0 = in0; cx.in1 = in1; cx.in2 = in2;
+            // ---- layer 1 (3 -> HP) on the CUDA cores ----
+            for (int nh = 0; nh < NHALF; ++nh) {
+                const int nfeat = min(256, HP - 256 * nh), ncols = nfeat >> 1, f0 = 256 * nh + ch * ncols;
+                first_layer_half(cx, f0, ncols, NM == 0, nh, out_acc);
+            }
+            // ---- hidden layers 2..NH ----
+            for (int m = 0; m < NM; ++m, ++use) {
+                const float oscale = __ldg(net.out_scale + m);
+                const float *bias = net.b_hidden + (size_t)(m + 1) * HP;
+                for (int nh = 0; nh < NHALF; ++nh, ++duse) {
+                    const int nfeat = min(256, HP - 256 * nh), ncols = nfeat >> 1, f0 = 256 * nh + ch * ncols;
+                    { DBG_T0(); mbar_wait(d_full, duse & 1); if (warp == 2 && lane == 0) DBG_ADD(4); }
+                    tc_fence_after();
+                    uint32_t d[4][32];
+#ifdef IKB_TC_DEBUG
+                    const long long _te = clock64();
+#endif
+                    const uint32_t taddr = tmem_base + lane_base + TMEM_D_COL + ch * ncols;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+                        if (q * 32 < ncols)
+                            tmem_ld32(taddr + q * 32, d[q]);
+                    tmem_ld_wait();
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0)
+                        mbar_arrive(d_empty);
+                    finish_half<false>(cx, d, f0, ncols, m == NM - 1, true, use & 1, nh, oscale, bias, out_acc);
+#ifdef IKB_TC_DEBUG
+                    if (blockIdx.x == 0 && warp == 2 && lane == 0) g_tc2_dbg[6] += (unsigned long long)(clock64() - _te);
+#endif
+                }
+            }
+            // ---- output layer: combine the two column halves, bias, y_scaler.inverse_transform (ann.py:71-75) ----
+            asm volatile("bar.sync 1, %0;" ::"n"(N_EPI_WARPS * 32));  // s_io inputs are no longer needed
+            if (ch == 1)
+                *reinterpret_cast<float4 *>(s_io + row * 4) = make_float4(out_acc[0], out_acc[1], out_acc[2], out_acc[3]);
+            asm volatile("bar.sync 1, %0;" ::"n"(N_EPI_WARPS * 32));
+            if (ch == 0 && row0 + row < a.n) {
+                const float4 other = *reinterpret_cast<const float4 *>(s_io + row * 4);
+                float yv[4] = {out_acc[0] + other.x, out_acc[1] + other.y, out_acc[2] + other.z, out_acc[3] + other.w};
+#pragma unroll
+                for (int o = 0; o < 4; ++o) {
+                    yv[o] += net.b_last[o];
+                    yv[o] = __fmul_rn(yv[o], net.scale_y[o]);
+                    yv[o] = __fadd_rn(yv[o], net.mean_y[o]);
+                }
+                reinterpret_cast<float4 *>(a.out)[row0 + row] = make_float4(yv[0], yv[1], yv[2], yv[3]);
+            }
+            asm volatile("bar.sync 1, %0;" ::"n"(N_EPI_WARPS * 32));
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+}
+
+size_t tc2_smem_bytes(int hp)
+{
+    return (size_t)(hp / 64) * GRAN_BYTES + (size_t)W_STAGES * WTILE_BYTES + ROWS * 4 * sizeof(float) + 16 * 8 + 64;
+}
+
+}  // namespace
+
+struct IkbMlpTc2 {
+    bool usable = false;
+    std::string why;
+    Tc2Net net;
+    void *arena = nullptr;
+};
+
+IkbMlpTc2 *ikb_mlp_tc2_new() { return new IkbMlpTc2(); }
+void ikb_mlp_tc2_delete(IkbMlpTc2 *t)
+{
+    if (t) {
+        if (t->arena)
+            cudaFree(t->arena);
+        delete t;
+    }
+}
+
+int ikb_mlp_tc2_pack(IkbMlpTc2 &t, int n_layers, const int *dims, const float *const *weights,
+                     const float *const *biases, const double mean_x[3], const double scale_x[3],
+                     const double mean_y[4], const double scale_y[4], std::string &err)
+{
+    if (t.arena)
+        cudaFree(t.arena);
+    t.arena = nullptr;
+    t.usable = false;
+    const int nh = n_layers - 1;
+    if (nh < 1) {
+        t.why = "needs at least one hidden layer";
+        return IKB_OK;
+    }
+    int hmax = 0;
+    for (int l = 1; l <= nh; ++l)
+        hmax = dims[l] > hmax ? dims[l] : hmax;
+    const int hp = ((hmax + 127) / 128) * 128;
+    const int KG = hp / 64, NHALF = (hp + 255) / 256, NM = nh - 1;
+    const size_t tile_halfs = WTILE_BYTES / sizeof(__half);
+    const size_t n_tiles = (size_t)NM * NHALF * KG * 2;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) / 256 * 256; return o; };
+    const size_t o_tiles = take((n_tiles ? n_tiles : 1) * WTILE_BYTES);
+    const size_t o_first = take((size_t)3 * hp * sizeof(float));
+    const size_t o_bias = take((size_t)(1 + NM) * hp * sizeof(float));
+    const size_t o_scale = take((size_t)(NM > 0 ? NM : 1) * sizeof(float));
+    const size_t o_last = take((size_t)hp * 4 * sizeof(float));
+    std::vector<unsigned char> host(off, 0);
+    __half *tiles = reinterpret_cast<__half *>(host.data() + o_tiles);
+    float *wfirst = reinterpret_cast<float *>(host.data() + o_first);
+    float *bias = reinterpret_cast<float *>(host.data() + o_bias);
+    float *oscale = reinterpret_cast<float *>(host.data() + o_scale);
+    float *wlast = reinterpret_cast<float *>(host.data() + o_last);
+    for (int k = 0; k < 3; ++k)
+        for (int f = 0; f < dims[1]; ++f)
+            wfirst[(size_t)k * hp + f] = weights[0][(size_t)k * dims[1] + f];
+    for (int l = 0; l < nh; ++l)
+        for (int f = 0; f < dims[l + 1]; ++f)
+            bias[(size_t)l * hp + f] = biases[l][f];
+    for (int m = 0; m < NM; ++m) {
+        const int l = m + 1, fin = dims[l], fout = dims[l + 1];
+        float wmax = 0.f;
+        for (size_t i = 0; i < (size_t)fin * fout; ++i)
+            wmax = std::fmax(wmax, std::fabs(weights[l][i]));
+        int e = 0;
+        if (wmax > 0.f)
+            e = 12 - (int)std::ceil(std::log2(wmax));  // largest weight near 2^12: w_lo stays normal, sums stay small
+        e = e > 24 ? 24 : (e < -8 ? -8 : e);
+        const float sw = std::ldexp(1.0f, e);
+        oscale[m] = 1.0f / (sw * X_SCALE);
+        for (int nhalf = 0; nhalf < NHALF; ++nhalf)
+            for (int kc = 0; kc < KG; ++kc) {
+                __half *hi = tiles + (((size_t)(m * NHALF + nhalf) * KG + kc) * 2 + 0) * tile_halfs;
+                __half *lo = hi + tile_halfs;
+                const int nfeat = std::min(256, hp - 256 * nhalf);
+                for (int r = 0; r < nfeat; ++r)
+                    for (int c = 0; c < 64; ++c) {
+                        const int f = nhalf * 256 + r, k = kc * 64 + c;
+                        const float w = (f < fout && k < fin) ? weights[l][(size_t)k * fout + f] * sw : 0.f;
+                        const __half h = __float2half_rn(w);
+                        const int o = swz_off(r, c) / 2;
+                        hi[o] = h;
+                        lo[o] = __float2half_rn(w - __half2float(h));
+                    }
+            }
+    }
+    for (int k = 0; k < dims[nh]; ++k)
+        for (int o = 0; o < 4; ++o)
+            wlast[(size_t)k * 4 + o] = weights[nh][(size_t)k * 4 + o];
+    cudaError_t ce = cudaMalloc(&t.arena, off);
+    if (ce == cudaSuccess)
+        ce = cudaMemcpy(t.arena, host.data(), off, cudaMemcpyHostToDevice);
+    if (ce != cudaSuccess) {
+        err = std::string("ikb_mlp_load (TS pack): ") + cudaGetErrorString(ce);
+        return IKB_ERR_CUDA;
+    }
+    Tc2Net &n = t.net;
+    memset(&n, 0, sizeof n);
+    n.n_mma_layers = NM;
+    n.hp = hp;
+    n.w_tiles = reinterpret_cast<const __half *>((char *)t.arena + o_tiles);
+    n.w_first = reinterpret_cast<const float *>((char *)t.arena + o_first);
+    n.b_hidden = reinterpret_cast<const float *>((char *)t.arena + o_bias);
+    n.out_scale = reinterpret_cast<const float *>((char *)t.arena + o_scale);
+    n.w_last = reinterpret_cast<const float *>((char *)t.arena + o_last);
+    for (int o = 0; o < 4; ++o) {
+        n.b_last[o] = biases[nh][o];
+        n.mean_y[o] = (float)mean_y[o];
+        n.scale_y[o] = (float)scale_y[o];
+    }
+    for (int j = 0; j < 3; ++j) {
+        n.mean_x[j] = mean_x[j];
+        n.scale_x[j] = scale_x[j];
+    }
+    ce = cudaFuncSetAttribute(mlp_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc2_smem_bytes(hp));
+    if (ce != cudaSuccess) {
+        err = std::string("ikb_mlp_load (TS smem attribute): ") + cudaGetErrorString(ce);
+        return IKB_ERR_CUDA;
+    }
+    t.usable = true;
+    return IKB_OK;
+}
+
+int ikb_mlp_tc2_launch(const IkbMlpTc2 &t, const void *xyz, int xyz_f64, long long n, long long index_base,
+                       float *angles_out, IkbDeviceStats *stats, const IkbRobot &rc, int num_sms,
+                       cudaStream_t stream, std::string &err)
+{
+    if (!t.usable) {
+        err = "IKB_MLP_FP16X3_TS: this network cannot use the tensor-core path (" + t.why + ")";
+        return IKB_ERR_UNSUPPORTED;
+    }
+    Tc2Args a;
+    a.xyz = xyz; a.xyz_f64 = xyz_f64; a.n = n; a.index_base = index_base; a.out = angles_out;
+    a.stats = stats; a.rc = rc; a.net = t.net;
+    const long long tiles = (n + ROWS - 1) / ROWS;
+    const unsigned grid = (unsigned)(tiles < num_sms ? tiles : num_sms);
+    mlp_tc2_kernel<<<grid, THREADS, tc2_smem_bytes(t.net.hp), stream>>>(a);
+    const cudaError_t ce = cudaGetLastError();
+    if (ce != cudaSuccess) {
+        err = std::string("mlp_tc2_kernel launch: ") + cudaGetErrorString(ce);
+        return IKB_ERR_CUDA;
+    }
+    return IKB_OK;
+}
+
+#ifdef IKB_TC_DEBUG
+extern "C" void ikbdbg_tc2_counters(unsigned long long *out, int reset)
+{
+    cudaMemcpyFromSymbol(out, g_tc2_dbg, sizeof(unsigned long long) * 16);
+    if (reset) {
+        unsigned long long z[16] = {0};
+        cudaMemcpyToSymbol(g_tc2_dbg, z, sizeof z);
+    }
+}
+#endif

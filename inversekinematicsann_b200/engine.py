@@ -302,7 +302,8 @@ class IkEngine:
         self.stats_reset(_torch_stream_ptr(self.device))
 
 
-_MLP_MODES = {"fp32": _native.IKB_MLP_FP32_SIMT, "fp16x3": _native.IKB_MLP_FP16X3_TC}
+_MLP_MODES = {"fp32": _native.IKB_MLP_FP32_SIMT, "fp16x3": _native.IKB_MLP_FP16X3_TC,
+              "fp16x3_ts": _native.IKB_MLP_FP16X3_TS}
 
 # algorithmic work per unit (SURVEY 8d / DESIGN.md), used by bench.py's roofline arithmetic
 FABRIK_FLOPS_PER_ITERATION = 114

@@ -17,7 +17,7 @@ for ci, (dims, n) in enumerate(cases):
     want = np_oracle.mlp_predict(xyz, W, b)
     want64 = np_oracle.mlp_predict(xyz, W, b, dtype=np.float64)
     t0 = time.time()
-    got, st = eng.ann_solve(xyz, mode="fp16x3")
+    got, st = eng.ann_solve(xyz, mode=os.environ.get("TC_MODE", "fp16x3"))
     ref32, _ = eng.ann_solve(xyz, mode="fp32")
     print(f"case {ci} dims {dims[:3]}..x{len(dims)-2} n {n}: tc vs fp32-oracle {np.abs(got-want).max():.3e} vs fp64 {np.abs(got-want64).max():.3e} "
           f"| simt vs fp64 {np.abs(ref32-want64).max():.3e} | nan {np.isnan(got).sum()} ({time.time()-t0:.2f}s)", flush=True)
