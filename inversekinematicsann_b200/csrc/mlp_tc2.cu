@@ -39,7 +39,13 @@ constexpr int ROWS = 128;             // targets per CTA tile = UMMA M
 constexpr int GRAN_BYTES = 16384;     // x_lo granule: 128 rows x 64 k x fp16
 constexpr int WTILE_BYTES = 32768;    // weight tile: up to 256 features x 64 k x fp16
 constexpr int W_STAGES = 3;
-constexpr int N_EPI_WARPS = 8;
+#ifndef IKB_TS_EPI_WARPS
+#define IKB_TS_EPI_WARPS 16
+#endif
+constexpr int N_EPI_WARPS = IKB_TS_EPI_WARPS;   // CW warps share the columns of one TMEM sub-partition
+constexpr int CW = N_EPI_WARPS / 4;
+static_assert(CW == 4, "the act_ready granularity (128 features) assumes 4 warps per TMEM sub-partition");
+constexpr int QMAX = 256 / CW / 32;             // groups of 32 accumulator columns per thread and N half
 constexpr int THREADS = (2 + N_EPI_WARPS) * 32;
 constexpr float X_SCALE = 64.0f;      // activations are stored times 2^6
 constexpr int TMEM_A_COL = 0, TMEM_D_COL = 256;
@@ -148,6 +154,9 @@ __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.
 // fix-ups (e is in (0, 1], 1 + e in (1, 2]); absolute error ~1e-7
 __device__ __forceinline__ float fast_tanh(float x)
 {
+#ifdef IKB_TS_ACCURATE_TANH
+    return tanhf(x);
+#endif
     float e, r;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-2.8853900817779268f * fabsf(x)));
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
@@ -182,15 +191,9 @@ struct EpiCtx {
     float in0, in1, in2;   // scaled inputs of this thread's row (first layer)
 };
 
-// One N half of one layer for one thread: `ncols` (64 or 128) features starting at f0.
-// FIRST: pre-activations come from the 3 inputs (layer 1, CUDA cores, libm tanhf); otherwise from the fp32
-// accumulators `d` (already in registers).  Results are packed IN PLACE over `d` (word 2t = the x_hi pair of
-// features 2t, 2t+1 of that group of 32, word 2t+1 = the x_lo pair), so no second register array is needed;
-// they become the next layer's x_hi (TMEM) / x_lo (smem), or, for the last hidden layer, go straight into the 4
-// output sums (the output layer needs fp32 activations anyway).
-// Layer 1 (3 -> HP) for one thread and one N half: a rolled loop over chunks of 8 features, stored at once
-// (nothing reads the activation buffers while a tile's first layer runs), or fed to the output sums when the
-// network has a single hidden layer.
+// Layer 1 (3 -> HP) for one thread: `ncols` features starting at f0, a rolled loop over chunks of 8 features
+// stored at once (nothing reads the activation buffers while a tile's first layer runs), or fed to the output sums
+// when the network has a single hidden layer.
 __device__ __forceinline__ void first_layer_half(const EpiCtx &cx, int f0, int ncols, bool last_hidden, int ready_idx,
                                                  float (&out_acc)[4])
 {
@@ -237,80 +240,96 @@ __device__ __forceinline__ void first_layer_half(const EpiCtx &cx, int f0, int n
         mbar_arrive(&cx.act_ready[ready_idx]);
 }
 
-template <bool FIRST>
-__device__ __forceinline__ void finish_half(const EpiCtx &cx, uint32_t (&d)[4][32], int f0, int ncols,
-                                            bool last_hidden, bool wait_free, uint32_t free_parity, int ready_idx,
+// One N half of one hidden layer for one thread.  The thread owns QMAX groups of 32 accumulator columns; group q
+// covers features fbase + q * 32 * CW .. + 31 (so that the CW warps of a sub-partition together complete 128
+// consecutive features = two k chunks of the next layer at a time, reported through act_ready[2 nh + q]).
+// Results are packed IN PLACE over `d` (word 2t = the x_hi pair of features 2t, 2t+1 of the group, word 2t+1 = the
+// x_lo pair); they become the next layer's x_hi (TMEM) / x_lo (smem), or, for the last hidden layer, go straight
+// into the 4 output sums (the output layer needs fp32 activations anyway).
+// early_compute: this is not the layer's last N half, i.e. the MMAs still read the old activations -- convert every
+// group first (overlapping the MMAs of the next half), then wait for a_free and store.  Otherwise a_free has fired
+// together with d_full: convert, store and report group by group so the next layer's MMAs can start on the first
+// 128 features while the second group is still being converted.
+__device__ __forceinline__ void finish_half(const EpiCtx &cx, uint32_t (&d)[QMAX][32], int fbase, int ngroups,
+                                            bool last_hidden, bool early_compute, uint32_t free_parity, int ready_base,
                                             float oscale, const float *bias, float (&out_acc)[4])
 {
     const Tc2Net &net = *cx.net;
+    auto convert = [&](int q) {
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        if (q * 32 < ncols) {
-#pragma unroll
-            for (int t = 0; t < 16; ++t) {
-                const int f = f0 + q * 32 + 2 * t;
-                float y0, y1;
-                if (FIRST) {
-                    y0 = tanhf(fmaf(cx.in2, __ldg(net.w_first + 2 * cx.HP + f),
-                                    fmaf(cx.in1, __ldg(net.w_first + cx.HP + f),
-                                         fmaf(cx.in0, __ldg(net.w_first + f), __ldg(net.b_hidden + f)))));
-                    y1 = tanhf(fmaf(cx.in2, __ldg(net.w_first + 2 * cx.HP + f + 1),
-                                    fmaf(cx.in1, __ldg(net.w_first + cx.HP + f + 1),
-                                         fmaf(cx.in0, __ldg(net.w_first + f + 1), __ldg(net.b_hidden + f + 1)))));
-                } else {
-                    y0 = fast_tanh(fmaf(__uint_as_float(d[q][2 * t]), oscale, __ldg(bias + f)));
-                    y1 = fast_tanh(fmaf(__uint_as_float(d[q][2 * t + 1]), oscale, __ldg(bias + f + 1)));
-                }
-                if (last_hidden) {
-                    const float4 w0 = __ldg(reinterpret_cast<const float4 *>(net.w_last) + f);
-                    const float4 w1 = __ldg(reinterpret_cast<const float4 *>(net.w_last) + f + 1);
-                    out_acc[0] = fmaf(y1, w1.x, fmaf(y0, w0.x, out_acc[0]));
-                    out_acc[1] = fmaf(y1, w1.y, fmaf(y0, w0.y, out_acc[1]));
-                    out_acc[2] = fmaf(y1, w1.z, fmaf(y0, w0.z, out_acc[2]));
-                    out_acc[3] = fmaf(y1, w1.w, fmaf(y0, w0.w, out_acc[3]));
-                } else {
-                    split_pair(y0, y1, d[q][2 * t], d[q][2 * t + 1]);
-                }
+        for (int t = 0; t < 16; ++t) {
+            const int f = fbase + q * 32 * CW + 2 * t;
+            const float y0 = fast_tanh(fmaf(__uint_as_float(d[q][2 * t]), oscale, __ldg(bias + f)));
+            const float y1 = fast_tanh(fmaf(__uint_as_float(d[q][2 * t + 1]), oscale, __ldg(bias + f + 1)));
+            if (last_hidden) {
+                const float4 w0 = __ldg(reinterpret_cast<const float4 *>(net.w_last) + f);
+                const float4 w1 = __ldg(reinterpret_cast<const float4 *>(net.w_last) + f + 1);
+                out_acc[0] = fmaf(y1, w1.x, fmaf(y0, w0.x, out_acc[0]));
+                out_acc[1] = fmaf(y1, w1.y, fmaf(y0, w0.y, out_acc[1]));
+                out_acc[2] = fmaf(y1, w1.z, fmaf(y0, w0.z, out_acc[2]));
+                out_acc[3] = fmaf(y1, w1.w, fmaf(y0, w0.w, out_acc[3]));
+            } else {
+                split_pair(y0, y1, d[q][2 * t], d[q][2 * t + 1]);
             }
         }
-    }
-    if (last_hidden)
+    };
+    auto store = [&](int q) {
+        const int f0 = fbase + q * 32 * CW;
+        // x_hi pairs of this group -> 16 TMEM columns
+        asm volatile(
+            "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, "
+            "%15, %16};" ::"r"(cx.tmem_base + cx.lane_base + TMEM_A_COL + (f0 >> 1)),
+            "r"(d[q][0]), "r"(d[q][2]), "r"(d[q][4]), "r"(d[q][6]), "r"(d[q][8]), "r"(d[q][10]), "r"(d[q][12]),
+            "r"(d[q][14]), "r"(d[q][16]), "r"(d[q][18]), "r"(d[q][20]), "r"(d[q][22]), "r"(d[q][24]), "r"(d[q][26]),
+            "r"(d[q][28]), "r"(d[q][30])
+            : "memory");
+        // x_lo pairs -> shared memory, 16-byte chunks of 8 features, swizzled K-major rows
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const int f = f0 + c * 8;
+            unsigned char *dst = cx.xlo + (size_t)(f >> 6) * GRAN_BYTES + cx.row * 128 +
+                                 (((((f & 63) >> 3) ^ (cx.row & 7)) & 7) << 4);
+            *reinterpret_cast<uint4 *>(dst) = make_uint4(d[q][8 * c + 1], d[q][8 * c + 3], d[q][8 * c + 5], d[q][8 * c + 7]);
+        }
+        tmem_st_wait();
+        fence_proxy_async();
+        tc_fence_before();
+        __syncwarp();
+        if (cx.lane == 0)
+            mbar_arrive(&cx.act_ready[ready_base + q]);
+    };
+    if (last_hidden) {
+#pragma unroll
+        for (int q = 0; q < QMAX; ++q)
+            if (q < ngroups)
+                convert(q);
         return;
-    if (wait_free) {
-        DBG_T0();
-        mbar_wait(cx.a_free, free_parity);  // the MMAs of this layer no longer read x_hi / x_lo
-        if (threadIdx.x == 64) DBG_ADD(5);
     }
-    tc_fence_after();
-    const uint32_t a_addr = cx.tmem_base + cx.lane_base + TMEM_A_COL + (f0 >> 1);
+    if (early_compute) {
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        if (q * 32 < ncols) {
-            // x_hi pairs of this group -> 16 TMEM columns
-            asm volatile(
-                "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, "
-                "%15, %16};" ::"r"(a_addr + q * 16),
-                "r"(d[q][0]), "r"(d[q][2]), "r"(d[q][4]), "r"(d[q][6]), "r"(d[q][8]), "r"(d[q][10]), "r"(d[q][12]),
-                "r"(d[q][14]), "r"(d[q][16]), "r"(d[q][18]), "r"(d[q][20]), "r"(d[q][22]), "r"(d[q][24]), "r"(d[q][26]),
-                "r"(d[q][28]), "r"(d[q][30])
-                : "memory");
-            // x_lo pairs -> shared memory, 16-byte chunks of 8 features, swizzled K-major rows
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                const int f = f0 + q * 32 + c * 8;
-                unsigned char *dst = cx.xlo + (size_t)(f >> 6) * GRAN_BYTES + cx.row * 128 +
-                                     (((((f & 63) >> 3) ^ (cx.row & 7)) & 7) << 4);
-                *reinterpret_cast<uint4 *>(dst) =
-                    make_uint4(d[q][8 * c + 1], d[q][8 * c + 3], d[q][8 * c + 5], d[q][8 * c + 7]);
-            }
+        for (int q = 0; q < QMAX; ++q)
+            if (q < ngroups)
+                convert(q);
+        {
+            DBG_T0();
+            mbar_wait(cx.a_free, free_parity);  // the MMAs of this layer no longer read x_hi / x_lo
+            if (threadIdx.x == 64) DBG_ADD(5);
         }
+        tc_fence_after();
+#pragma unroll
+        for (int q = 0; q < QMAX; ++q)
+            if (q < ngroups)
+                store(q);
+    } else {
+        mbar_wait(cx.a_free, free_parity);
+        tc_fence_after();
+#pragma unroll
+        for (int q = 0; q < QMAX; ++q)
+            if (q < ngroups) {
+                convert(q);
+                store(q);
+            }
     }
-    tmem_st_wait();
-    fence_proxy_async();
-    tc_fence_before();
-    __syncwarp();
-    if (cx.lane == 0)
-        mbar_arrive(&cx.act_ready[ready_idx]);
 }
 
 __global__ void __launch_bounds__(THREADS, 1) mlp_tc2_kernel(const Tc2Args a)
@@ -324,8 +343,8 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_tc2_kernel(const Tc2Args a)
     uint64_t *bars = reinterpret_cast<uint64_t *>(s_io + ROWS * 4);
     uint64_t *w_full = bars, *w_empty = bars + W_STAGES;
     uint64_t *d_full = w_empty + W_STAGES, *d_empty = d_full + 1;   // the single accumulator: MMA <-> epilogue
-    uint64_t *act_ready = d_empty + 1;                              // [2] epilogue -> MMA: k half of the next input stored
-    uint64_t *a_free = act_ready + 2;                               // MMA -> epilogue: this layer's input is dead
+    uint64_t *act_ready = d_empty + 1;                              // [4] epilogue -> MMA: 128 features (2 k chunks) of the next input stored
+    uint64_t *a_free = act_ready + 4;                               // MMA -> epilogue: this layer's input is dead
     uint32_t *s_tmem = reinterpret_cast<uint32_t *>(a_free + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -336,8 +355,8 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_tc2_kernel(const Tc2Args a)
         }
         mbar_init(d_full, 1);
         mbar_init(d_empty, N_EPI_WARPS);
-        mbar_init(&act_ready[0], N_EPI_WARPS);
-        mbar_init(&act_ready[1], N_EPI_WARPS);
+        for (int i = 0; i < 4; ++i)
+            mbar_init(&act_ready[i], N_EPI_WARPS);
         mbar_init(a_free, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -393,8 +412,8 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_tc2_kernel(const Tc2Args a)
                         { DBG_T0(); mbar_wait(d_empty, (duse & 1) ^ 1); DBG_ADD(3); }  // the epilogue has drained the accumulator
                         tc_fence_after();
                         for (int kc = 0; kc < KG; ++kc) {
-                            if (nh == 0 && (kc & 3) == 0) {  // k half kc/4 of this layer's input has been stored
-                                { DBG_T0(); mbar_wait(&act_ready[kc >> 2], use & 1); DBG_ADD(2); }
+                            if (nh == 0 && (kc & 1) == 0) {  // features 64 kc .. 64 kc + 127 of this layer's input are stored
+                                { DBG_T0(); mbar_wait(&act_ready[kc >> 1], use & 1); DBG_ADD(2); }
                                 tc_fence_after();
                             }
                             const uint32_t a_cols = a_tmem + kc * 32;  // 64 k = 32 columns of packed fp16 pairs
@@ -434,7 +453,7 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_tc2_kernel(const Tc2Args a)
         // ===== epilogue warps: thread = (batch row = TMEM lane, half of the columns of the N half) =====
         const int ew = warp - 2;
         const int sub = warp & 3;             // TMEM sub-partition this warp may access
-        const int ch = ew >> 2;               // column half
+        const int ch = ew >> 2;               // column group (0 .. CW-1) within the N half
         const int row = sub * 32 + lane;      // batch row within the tile
         const int et = ew * 32 + lane;
         const uint32_t lane_base = (uint32_t)(sub * 32) << 16;
@@ -465,32 +484,34 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_tc2_kernel(const Tc2Args a)
             cx.lane_base = lane_base; cx.row = row; cx.lane = lane; cx.HP = HP; cx.in0 = in0; cx.in1 = in1; cx.in2 = in2;
             // ---- layer 1 (3 -> HP) on the CUDA cores ----
             for (int nh = 0; nh < NHALF; ++nh) {
-                const int nfeat = min(256, HP - 256 * nh), ncols = nfeat >> 1, f0 = 256 * nh + ch * ncols;
-                first_layer_half(cx, f0, ncols, NM == 0, nh, out_acc);
+                const int ngroups = min(256, HP - 256 * nh) / (32 * CW);
+                for (int q = 0; q < ngroups; ++q)
+                    first_layer_half(cx, 256 * nh + q * 32 * CW + 32 * ch, 32, NM == 0, 2 * nh + q, out_acc);
             }
             // ---- hidden layers 2..NH ----
             for (int m = 0; m < NM; ++m, ++use) {
                 const float oscale = __ldg(net.out_scale + m);
                 const float *bias = net.b_hidden + (size_t)(m + 1) * HP;
                 for (int nh = 0; nh < NHALF; ++nh, ++duse) {
-                    const int nfeat = min(256, HP - 256 * nh), ncols = nfeat >> 1, f0 = 256 * nh + ch * ncols;
+                    const int ngroups = min(256, HP - 256 * nh) / (32 * CW);
                     { DBG_T0(); mbar_wait(d_full, duse & 1); if (warp == 2 && lane == 0) DBG_ADD(4); }
                     tc_fence_after();
-                    uint32_t d[4][32];
+                    uint32_t d[QMAX][32];
 #ifdef IKB_TC_DEBUG
                     const long long _te = clock64();
 #endif
-                    const uint32_t taddr = tmem_base + lane_base + TMEM_D_COL + ch * ncols;
+                    const uint32_t taddr = tmem_base + lane_base + TMEM_D_COL + 32 * ch;
 #pragma unroll
-                    for (int q = 0; q < 4; ++q)
-                        if (q * 32 < ncols)
-                            tmem_ld32(taddr + q * 32, d[q]);
+                    for (int q = 0; q < QMAX; ++q)
+                        if (q < ngroups)
+                            tmem_ld32(taddr + q * 32 * CW, d[q]);
                     tmem_ld_wait();
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0)
                         mbar_arrive(d_empty);
-                    finish_half<false>(cx, d, f0, ncols, m == NM - 1, true, use & 1, nh, oscale, bias, out_acc);
+                    finish_half(cx, d, 256 * nh + 32 * ch, ngroups, m == NM - 1, nh + 1 < NHALF, use & 1, 2 * nh, oscale,
+                                bias, out_acc);
 #ifdef IKB_TC_DEBUG
                     if (blockIdx.x == 0 && warp == 2 && lane == 0) g_tc2_dbg[6] += (unsigned long long)(clock64() - _te);
 #endif
@@ -498,9 +519,20 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_tc2_kernel(const Tc2Args a)
             }
             // ---- output layer: combine the two column halves, bias, y_scaler.inverse_transform (ann.py:71-75) ----
             asm volatile("bar.sync 1, %0;" ::"n"(N_EPI_WARPS * 32));  // s_io inputs are no longer needed
-            if (ch == 1)
-                *reinterpret_cast<float4 *>(s_io + row * 4) = make_float4(out_acc[0], out_acc[1], out_acc[2], out_acc[3]);
-            asm volatile("bar.sync 1, %0;" ::"n"(N_EPI_WARPS * 32));
+            // column groups 1 .. CW-1 add their partial sums into s_io one after the other, group 0 finishes
+#pragma unroll
+            for (int g = 1; g < CW; ++g) {
+                if (ch == g) {
+                    float4 *slot = reinterpret_cast<float4 *>(s_io + row * 4);
+                    float4 v = make_float4(out_acc[0], out_acc[1], out_acc[2], out_acc[3]);
+                    if (g > 1) {
+                        const float4 o = *slot;
+                        v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
+                    }
+                    *slot = v;
+                }
+                asm volatile("bar.sync 1, %0;" ::"n"(N_EPI_WARPS * 32));
+            }
             if (ch == 0 && row0 + row < a.n) {
                 const float4 other = *reinterpret_cast<const float4 *>(s_io + row * 4);
                 float yv[4] = {out_acc[0] + other.x, out_acc[1] + other.y, out_acc[2] + other.z, out_acc[3] + other.w};

@@ -75,7 +75,8 @@ class ANN:
         self.model = None
         self.x_data_skaler = None  # attribute names as upstream (ann.py:24-25)
         self.y_data_skaler = None
-        self.mode = 'fp16x3'  # 'fp16x3': tcgen05 split-fp16 tensor-core kernel; 'fp32': CUDA-core kernel
+        # 'fp16x3_ts' (default) / 'fp16x3': tcgen05 split-fp16 tensor-core kernels; 'fp32': CUDA-core kernel
+        self.mode = 'fp16x3_ts'
         self._device = device
         self._uploaded = False
 

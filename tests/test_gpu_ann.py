@@ -10,10 +10,11 @@ pytestmark = pytest.mark.gpu
 TOL_NORTH_STAR = 1e-5  # rad
 
 
-MODES = ["fp16x3", "fp32"]  # tcgen05 split-fp16 tensor-core kernel (default) and fp32 CUDA-core kernel
+# tcgen05 split-fp16 kernels (TS: activations in TMEM, default; SS: activations in smem) and the fp32 CUDA-core kernel
+MODES = ["fp16x3_ts", "fp16x3", "fp32"]
 
 
-def _make(dims, seed, mode="fp16x3"):
+def _make(dims, seed, mode="fp16x3_ts"):
     from inversekinematicsann_b200.kinematics.inverse import AnnInverseKinematics
     from inversekinematicsann_b200.robot.robot import SixDOFRobot as R
     from oracle import np_oracle
@@ -48,8 +49,8 @@ def test_full_architecture_vs_fp32_oracle(mode):
 
 
 @pytest.mark.parametrize("mode", MODES)
-@pytest.mark.parametrize("n", [1, 63, 64, 65, 1000, 148 * 64 + 5])
-@pytest.mark.parametrize("dims", [[3, 64, 4], [3, 100, 50, 4], [3, 300, 300, 4], [3, 500, 500, 500, 4]])
+@pytest.mark.parametrize("n", [1, 63, 64, 65, 129, 1000, 148 * 128 + 5])
+@pytest.mark.parametrize("dims", [[3, 64, 4], [3, 100, 50, 4], [3, 200, 256, 4], [3, 300, 300, 4], [3, 500, 500, 500, 4]])
 def test_ragged_sizes_and_small_nets(n, dims, mode):
     from oracle import np_oracle
     ann, W, b = _make(dims, seed=7, mode=mode)
@@ -99,11 +100,12 @@ def test_modes_agree_and_are_deterministic():
     """The two arithmetic modes are independent implementations of the same network: they must agree
     with each other as well as with the oracle, and repeated launches must be bit-identical."""
     from oracle import np_oracle
-    ann, W, b = _make(np_oracle.LAYER_DIMS, seed=99, mode="fp16x3")
+    ann, W, b = _make(np_oracle.LAYER_DIMS, seed=99, mode="fp32")
     xyz = _points(30_000, seed=5)
-    a1 = ann.ikine(xyz, as_array=True).copy()
-    a2 = ann.ikine(xyz, as_array=True).copy()
-    assert np.array_equal(a1, a2)
-    ann.ann.mode = "fp32"
-    s1 = ann.ikine(xyz, as_array=True)
-    assert np.abs(a1 - s1).max() <= TOL_NORTH_STAR
+    s1 = ann.ikine(xyz, as_array=True).copy()
+    for mode in ("fp16x3_ts", "fp16x3"):
+        ann.ann.mode = mode
+        a1 = ann.ikine(xyz, as_array=True).copy()
+        a2 = ann.ikine(xyz, as_array=True).copy()
+        assert np.array_equal(a1, a2), mode
+        assert np.abs(a1 - s1).max() <= TOL_NORTH_STAR, mode

@@ -16,7 +16,7 @@ eng.ann_solve_device(xyz, out, mode="fp16x3_ts"); torch.cuda.synchronize()
 lib.ikbdbg_tc2_counters(buf, 1)
 eng.ann_solve_device(xyz, out, mode="fp16x3_ts"); torch.cuda.synchronize()
 lib.ikbdbg_tc2_counters(buf, 1)
-names = ["mma_total", "mma_wait_w_full", "mma_wait_act_ready", "mma_wait_d_empty", "epi_wait_d_full", "epi_wait_a_free", "epi_half_total"]
+names = ["mma_total", "mma_wait_w_full", "mma_wait_act_ready", "mma_wait_d_empty", "epi_wait_d_full", "epi_wait_a_free", "epi_half_total", "epi_compute", "epi_waitfree+store", "epi_drain"]
 tiles = 20
 for n, v in zip(names, buf):
     print(f"{n:22s} {v:12d} cycles  per layer {v / tiles / 11:10.0f}")
