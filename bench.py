@@ -375,6 +375,29 @@ def main():
         sampler.stop()
         clocks = sampler.summary(w0, w1)
 
+    # ---- the other BASELINE configs as drop-in latency / wire-path figures (rank 0, not part of `value`) ----
+    extras = None
+    if rank == 0:
+        from inversekinematicsann_b200 import wire
+        from inversekinematicsann_b200.robot.position_generator import TrainingDataGenerator as G
+        spring = G.spring(50, 2, 3, 6)                      # configs[0]: cli.py --shape spring example (cli.py:195)
+        ik.ikine(spring)
+        t0 = time.perf_counter()
+        for _ in range(20):
+            ik.ikine(spring)                                # list in, list out, exactly the CLI's call
+        spring_ms = (time.perf_counter() - t0) / 20 * 1e3
+        circ = G.circle_device(2, 10_000_000, (2, 0, 2), dtype="float32").cpu().numpy()   # configs[4]
+        body = wire.encode_binary_request(circ)
+        wire.handle_request(ik, body)
+        t0 = time.perf_counter()
+        reply = wire.handle_request(ik, body)
+        broker_s = time.perf_counter() - t0
+        extras = {"cli_spring_50_points_ms": spring_ms,
+                  "cli_spring_reference_ms": "~30 (1 678 solves/s, BASELINE.md)",
+                  "broker_binary_10M_circle": {"value": 10_000_000 / broker_s, "unit": UNIT,
+                                               "request_bytes": len(body), "reply_bytes": len(reply),
+                                               "path": "wire.handle_request(IKB1 payload) = decode + ikine + encode, pageable host buffers"}}
+
     cpu_baseline = None
     if rank == 0 and not args.skip_cpu:
         sample, threads = calibrated_cpu_sample(WORKSPACE_BOX)
@@ -400,6 +423,7 @@ def main():
                        "sharding": f"contiguous ranges, {world} rank(s), no data-path collective"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(gpu_launches), "roofline": roofline,
             "cpu_baseline": cpu_baseline, "fk_error": fk_error, "fabrik_interior_box": interior, "ann": ann_block,
+            "other_configs": extras,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

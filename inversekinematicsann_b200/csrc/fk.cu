@@ -110,12 +110,18 @@ struct FkArgs {
     IkbRobot rc;
 };
 
-// FK_ROWS rows per thread and loop trip, all of their loads issued before any arithmetic: at 28 B of
+// FK_ROWS rows per thread and loop trip (2 rows x 4 resident CTAs measured best), all of their loads issued
+// before any arithmetic: at 28 B of
 // input per row the kernel needs ~5 MB in flight chip-wide to cover HBM latency.
-#define FK_ROWS 4
+#ifndef FK_ROWS
+#define FK_ROWS 2
+#endif
+#ifndef FK_MINB
+#define FK_MINB 4
+#endif
 
 template <typename Real>
-__global__ void __launch_bounds__(256) fk_kernel(const FkArgs a)
+__global__ void __launch_bounds__(256, FK_MINB) fk_kernel(const FkArgs a)
 {
     const long long stride = (long long)gridDim.x * blockDim.x;
     double err_sum = 0.0;
