@@ -205,3 +205,72 @@ def test_full_size_properties():
     eng.fabrik_solve_device(xyz, out2)
     torch.cuda.synchronize()
     assert torch.equal(out.view(torch.int32), out2.view(torch.int32))
+
+
+@pytest.mark.parametrize("tol,max_iter", [(1e-2, 100), (1e-3, 10), (1e-5, 30), (1e-3, 1)])
+def test_non_default_solver_parameters(robot, tol, max_iter):
+    """max_err / max_iterations_num of FabrikInverseKinematics (inverse.py:47-48) reach the kernel."""
+    from inversekinematicsann_b200.kinematics.inverse import FabrikInverseKinematics
+    from oracle import c_oracle
+    rng = np.random.RandomState(11)
+    xyz = rng.rand(20_000, 3) * [6, 12, 9] + [0, -6, -3]
+    ik2 = FabrikInverseKinematics(robot.dh_matrix, robot.links_lengths, robot.effector_workspace_limits,
+                                  max_err=tol, max_iterations_num=max_iter)
+    angles, iters = ik2.ikine(xyz, as_array=True, return_iterations=True)
+    want = c_oracle.fabrik_ikine(xyz, tol=tol, max_iter=max_iter)
+    assert np.array_equal(iters, want["iters"]) and iters.max() <= max_iter
+    assert np.abs(angles - want["angles"]).max() <= TOL_F64_MODE
+
+
+def test_zero_iteration_corner(robot):
+    """tol >= 1 (or max_iter <= 0): the reference's while loop never runs and the seed chain is returned."""
+    from inversekinematicsann_b200.kinematics.inverse import FabrikInverseKinematics
+    from oracle import c_oracle
+    xyz = np.array([[1.0, 2.0, 3.0], [3.0, -1.0, 0.5]])
+    for kw in ({"max_err": 1.5}, {"max_iterations_num": 0}):
+        ikz = FabrikInverseKinematics(robot.dh_matrix, robot.links_lengths, robot.effector_workspace_limits, **kw)
+        angles, iters = ikz.ikine(xyz, as_array=True, return_iterations=True)
+        want = c_oracle.fabrik_ikine(xyz, tol=kw.get("max_err", 1e-3), max_iter=kw.get("max_iterations_num", 100))
+        assert (iters == 0).all() and (want["iters"] == 0).all()
+        # theta_1 of the vertical seed chain is atan2 of rounding noise upstream; the other angles are pinned
+        np.testing.assert_allclose(angles[:, 1:], want["angles"][:, 1:], rtol=0, atol=TOL_F64_MODE)
+
+
+def test_unequal_link_lengths(robot):
+    """joints_distances is independent of the DH table upstream (robot.py:42 vs :40)."""
+    from inversekinematicsann_b200.kinematics.inverse import FabrikInverseKinematics
+    from oracle import c_oracle
+    links = [2.0, 1.5, 2.5, 1.0]
+    rng = np.random.RandomState(12)
+    xyz = rng.rand(20_000, 3) * [4, 8, 6] + [0.5, -4, -1]
+    ikl = FabrikInverseKinematics(robot.dh_matrix, links, robot.effector_workspace_limits)
+    angles, iters = ikl.ikine(xyz, as_array=True, return_iterations=True)
+    want = c_oracle.fabrik_ikine(xyz, links=np.array(links))
+    ok = want["status"] == 0
+    assert np.array_equal(iters[ok], want["iters"][ok])
+    finite = ok & np.isfinite(want["angles"]).all(axis=1)
+    assert np.abs(angles[finite] - want["angles"][finite]).max() <= TOL_F64_MODE
+
+
+def test_rotation_about_z_only_moves_theta1(ik):
+    """The solve happens in the vertical plane through the z axis: rotating a target about z shifts theta_1 by
+    the same angle and leaves theta_2..4 unchanged (a property the 2-D reduction relies on)."""
+    rng = np.random.RandomState(13)
+    n = 50_000
+    r, phi = rng.uniform(0.5, 5.5, n), rng.uniform(-1.2, 1.2, n)
+    z = rng.uniform(-3, 6, n)
+    dphi = rng.uniform(-0.3, 0.3, n)
+    a = ik.ikine(np.stack([r * np.cos(phi), r * np.sin(phi), z], 1), as_array=True)
+    b = ik.ikine(np.stack([r * np.cos(phi + dphi), r * np.sin(phi + dphi), z], 1), as_array=True)
+    np.testing.assert_allclose(b[:, 0] - a[:, 0], dphi, rtol=0, atol=1e-9)
+    # near-straight joints quantise through round(cos, 8): allow one quantum there, exact-ish elsewhere
+    d = np.abs(b[:, 1:] - a[:, 1:])
+    assert np.percentile(d, 99.9) < 1e-9 and d.max() < 2e-4
+
+
+def test_float32_and_float64_inputs_agree(ik):
+    rng = np.random.RandomState(14)
+    xyz = (rng.rand(20_000, 3) * [2, 4, 3] + [1, -2, 1]).astype(np.float32)
+    a32 = ik.ikine(xyz, as_array=True)
+    a64 = ik.ikine(xyz.astype(np.float64), as_array=True)
+    assert np.array_equal(a32, a64)  # the same numbers reach the kernel either way
