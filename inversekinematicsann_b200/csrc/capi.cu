@@ -19,6 +19,9 @@ cudaError_t ikb_launch_fabrik_planar(const void *xyz, int xyz_f64, long long n, 
 cudaError_t ikb_launch_fabrik_generic(const double *init, long long n_init, const double *goals,
                                       long long n, double *chain_out, int *iters,
                                       IkbDeviceStats *stats, const IkbRobot &rc, cudaStream_t stream);
+cudaError_t ikb_launch_fabrik_generic_ikine(const void *xyz, int xyz_f64, long long n, long long index_base,
+                                            void *angles, int angles_f64, int *iters, IkbDeviceStats *stats,
+                                            const IkbRobot &rc, cudaStream_t stream);
 cudaError_t ikb_launch_fk(const void *angles, int angles_f64, long long n, long long index_base,
                           void *pos_out, const void *targets, int xyz_f64, void *err_out,
                           IkbDeviceStats *stats, const IkbRobot &rc, int num_sms, cudaStream_t stream);
@@ -372,14 +375,15 @@ int ikb_fabrik_solve_device(ikb_engine *e, const void *xyz, int xyz_dtype, int64
     if (!e || n < 0 || (n > 0 && (!xyz || !angles_out)) || bad_dtype(xyz_dtype) || bad_dtype(angles_dtype) ||
         (precision != IKB_FABRIK_F64 && precision != IKB_FABRIK_F32) || n > 0x7fffffffLL)
         return fail(e, IKB_ERR_INVALID, "ikb_fabrik_solve_device: bad argument (n must be < 2^31 per call)");
-    if (!e->rc.planar)
-        return fail(e, IKB_ERR_UNSUPPORTED,
-                    "FABRIK ikine needs a seed chain that lies in one vertical plane (alpha_1 = pi/2, "
-                    "other alphas 0, as in robot/robot.py); use ikb_fabrik_calculate_host for general chains");
     IKB_CUDA(e, cudaSetDevice(e->device));
-    IKB_CUDA(e, ikb_launch_fabrik_planar(xyz, xyz_dtype == IKB_F64, n, 0, angles_out, angles_dtype == IKB_F64,
-                                         iters_out, precision, e->d_stats, next_counter(e), e->rc,
-                                         e->num_sms, (cudaStream_t)stream));
+    if (!e->rc.planar)  // general DH table: the seed chain leaves the vertical plane -> 3-D kernel
+        IKB_CUDA(e, ikb_launch_fabrik_generic_ikine(xyz, xyz_dtype == IKB_F64, n, 0, angles_out,
+                                                    angles_dtype == IKB_F64, iters_out, e->d_stats, e->rc,
+                                                    (cudaStream_t)stream));
+    else
+        IKB_CUDA(e, ikb_launch_fabrik_planar(xyz, xyz_dtype == IKB_F64, n, 0, angles_out, angles_dtype == IKB_F64,
+                                             iters_out, precision, e->d_stats, next_counter(e), e->rc,
+                                             e->num_sms, (cudaStream_t)stream));
     e->launches += (n > 0);
     return IKB_OK;
 }
@@ -390,8 +394,6 @@ int ikb_fabrik_solve_host(ikb_engine *e, const void *xyz, int xyz_dtype, int64_t
     if (!e || n < 0 || (n > 0 && (!xyz || !angles_out)) || bad_dtype(xyz_dtype) || bad_dtype(angles_dtype) ||
         (precision != IKB_FABRIK_F64 && precision != IKB_FABRIK_F32))
         return fail(e, IKB_ERR_INVALID, "ikb_fabrik_solve_host: bad argument");
-    if (!e->rc.planar)
-        return fail(e, IKB_ERR_UNSUPPORTED, "FABRIK ikine needs a planar seed chain (see ikb_fabrik_solve_device)");
     int rc = host_begin(e, n);
     if (rc)
         return rc;
@@ -401,9 +403,14 @@ int ikb_fabrik_solve_host(ikb_engine *e, const void *xyz, int xyz_dtype, int64_t
         Slot &s = e->slots[it % kSlots];
         const long long m = std::min<long long>(kHostChunkRows, n - lo);
         IKB_CUDA(e, cudaMemcpyAsync(s.d_in, (const char *)xyz + lo * in_row, m * in_row, cudaMemcpyHostToDevice, s.stream));
-        IKB_CUDA(e, ikb_launch_fabrik_planar(s.d_in, xyz_dtype == IKB_F64, m, lo, s.d_out,
-                                             angles_dtype == IKB_F64, iters_out ? s.d_aux : nullptr,
-                                             precision, e->d_stats, next_counter(e), e->rc, e->num_sms, s.stream));
+        if (!e->rc.planar)
+            IKB_CUDA(e, ikb_launch_fabrik_generic_ikine(s.d_in, xyz_dtype == IKB_F64, m, lo, s.d_out,
+                                                        angles_dtype == IKB_F64, iters_out ? s.d_aux : nullptr,
+                                                        e->d_stats, e->rc, s.stream));
+        else
+            IKB_CUDA(e, ikb_launch_fabrik_planar(s.d_in, xyz_dtype == IKB_F64, m, lo, s.d_out,
+                                                 angles_dtype == IKB_F64, iters_out ? s.d_aux : nullptr,
+                                                 precision, e->d_stats, next_counter(e), e->rc, e->num_sms, s.stream));
         e->launches++;
         IKB_CUDA(e, cudaMemcpyAsync((char *)angles_out + lo * out_row, s.d_out, m * out_row, cudaMemcpyDeviceToHost, s.stream));
         if (iters_out)

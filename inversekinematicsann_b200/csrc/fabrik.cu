@@ -542,6 +542,111 @@ __global__ void __launch_bounds__(128) fabrik_generic_kernel(const FabrikGeneric
     atomicAdd(&a.stats->n_solved, 1ULL);
 }
 
+// ---- generic ikine: robots whose seed chain leaves the vertical plane (general DH tables) ----------------------
+// One target per thread, IEEE fp64 in 3-D with the reference's operation order: seed chain = the theta_1 = 0
+// chain rotated about z by atan2(y, x) (inverse.py:123-130), Fabrik.calculate (fabrik.py:44-67), __get_angles
+// (inverse.py:54-112).  Slower than the planar kernel (warp-vote exit, no lane refill) -- the reference's own
+// robot never takes this path.
+struct FabrikGenericIkineArgs {
+    const void *xyz;
+    int xyz_f64;
+    long long n;
+    long long index_base;
+    void *angles;
+    int angles_f64;
+    int *iters;
+    IkbDeviceStats *stats;
+    IkbRobot rc;
+};
+
+__global__ void __launch_bounds__(128) fabrik_generic_ikine_kernel(const FabrikGenericIkineArgs a)
+{
+    const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = tid < a.n;                 // lanes past the end redo the last row and write nothing,
+    const long long i = valid ? tid : a.n - 1;    // so the warp-wide reductions below see full warps
+    const IkbRobot &rc = a.rc;
+    const double PI = 3.141592653589793;
+    double x, y, z;
+    ikb_load_xyz(a.xyz, a.xyz_f64, i, x, y, z);
+    const long long row = a.index_base + i;
+    if (valid && ikb_out_of_limits(rc, x, y, z))
+        atomicMin(&a.stats->first_out_of_limits, row);
+    double s1, c1;
+    sincos(atan2(y, x), &s1, &c1);
+    Vec3 P[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const double sx = rc.seed_xyz[3 * j], sy = rc.seed_xyz[3 * j + 1];
+        P[j] = Vec3{sx * c1 - sy * s1, sx * s1 + sy * c1, rc.seed_xyz[3 * j + 2]};
+    }
+    const Vec3 S = P[0], T{x, y, z};
+    const double *d = rc.links;
+    double se = 1.0, ge = 1.0;
+    int step = 0;
+    while ((se > rc.tol || ge > rc.tol) && rc.max_iter > step) {
+        const Vec3 b2 = point_between3(T, P[2], d[2]);
+        const Vec3 b1 = point_between3(b2, P[1], d[1]);
+        const Vec3 b0 = point_between3(b1, P[0], d[0]);
+        se = dist3(b0, S);
+        P[0] = S;
+        P[1] = point_between3(P[0], b1, d[1]);
+        P[2] = point_between3(P[1], b2, d[2]);
+        P[3] = point_between3(P[2], T, d[3]);
+        ge = dist3(P[3], T);
+        ++step;
+    }
+    const Vec3 A{0.0, 0.0, 0.0};
+    const Vec3 &B = P[0], &C = P[1], &D = P[2], &E = P[3];
+    double th[4];
+    th[0] = atan2(E.y, E.x);
+    const double ab = dist3(A, B), bc = dist3(B, C), cd = dist3(C, D), de = dist3(D, E);
+    const double ac = dist3(A, C), bd = dist3(B, D), ce = dist3(C, E);
+    bool zero_div = false;
+    double den = 2 * ab * bc;
+    zero_div |= (den == 0.0);
+    const double c2 = round8((ab * ab + bc * bc - ac * ac) / den);
+    const double acos2 = acos(c2);
+    th[1] = (C.x * D.x < 0) ? (3 * PI / 2) - acos2 : -(PI / 2 - acos2);
+    den = 2 * bc * cd;
+    zero_div |= (den == 0.0);
+    const double c3 = round8((bc * bc + cd * cd - bd * bd) / den);
+    th[2] = -(PI - acos(c3));
+    den = 2 * cd * de;
+    zero_div |= (den == 0.0) | (ce == 0.0);
+    const double c4 = round8((cd * cd + de * de - ce * ce) / den);
+    const double acos4 = acos(c4);
+    const Vec3 mid = point_between3(C, E, ce / 2);
+    th[3] = (bd > dist3(B, mid)) ? -(PI - acos4) : (PI - acos4);
+    const bool finite_in = isfinite(x) & isfinite(y) & isfinite(z);
+    bool chain_nan = false;
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+        chain_nan |= !(isfinite(P[j].x) & isfinite(P[j].y) & isfinite(P[j].z));
+    zero_div = (zero_div | chain_nan) & finite_in;
+    const bool domain = !zero_div & (fabs(c2) > 1.0 | fabs(c3) > 1.0 | fabs(c4) > 1.0);
+    if (zero_div) {
+        th[0] = th[1] = th[2] = th[3] = __longlong_as_double(0x7ff8000000000000LL);
+        if (valid)
+            atomicMin(&a.stats->first_zero_division, row);
+    }
+    if (domain && valid)
+        atomicMin(&a.stats->first_domain_error, row);
+    if (valid) {
+        ikb_store_angles(a.angles, a.angles_f64, i, th);
+        if (a.iters)
+            a.iters[i] = step;
+    }
+    const bool more = (se > rc.tol) | (ge > rc.tol);
+    const unsigned long long it = ikb_warp_sum(valid ? (unsigned long long)step : 0ULL);
+    const unsigned sv = ikb_warp_sum(valid ? 1u : 0u), cp = ikb_warp_sum((valid && more && step > 0) ? 1u : 0u);
+    if ((threadIdx.x & 31) == 0 && sv != 0) {
+        atomicAdd(&a.stats->sum_iterations, it);
+        atomicAdd(&a.stats->n_solved, (unsigned long long)sv);
+        if (cp)
+            atomicAdd(&a.stats->n_iter_capped, (unsigned long long)cp);
+    }
+}
+
 }  // namespace
 
 // ---- launchers (called from capi.cu) --------------------------------------------------------------
@@ -569,6 +674,19 @@ cudaError_t ikb_launch_fabrik_planar(const void *xyz, int xyz_f64, long long n, 
         fabrik_planar_kernel<float, IKB_FABRIK_CHAINS><<<(unsigned)grid, per_cta, 0, stream>>>(a);
     else
         fabrik_planar_kernel<double, IKB_FABRIK_CHAINS><<<(unsigned)grid, per_cta, 0, stream>>>(a);
+    return cudaGetLastError();
+}
+
+cudaError_t ikb_launch_fabrik_generic_ikine(const void *xyz, int xyz_f64, long long n, long long index_base,
+                                            void *angles, int angles_f64, int *iters, IkbDeviceStats *stats,
+                                            const IkbRobot &rc, cudaStream_t stream)
+{
+    if (n <= 0)
+        return cudaSuccess;
+    FabrikGenericIkineArgs a;
+    a.xyz = xyz; a.xyz_f64 = xyz_f64; a.n = n; a.index_base = index_base; a.angles = angles;
+    a.angles_f64 = angles_f64; a.iters = iters; a.stats = stats; a.rc = rc;
+    fabrik_generic_ikine_kernel<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(a);
     return cudaGetLastError();
 }
 

@@ -274,3 +274,42 @@ def test_float32_and_float64_inputs_agree(ik):
     a32 = ik.ikine(xyz, as_array=True)
     a64 = ik.ikine(xyz.astype(np.float64), as_array=True)
     assert np.array_equal(a32, a64)  # the same numbers reach the kernel either way
+
+
+def test_other_planar_seed_pose():
+    """A different seed row / first-link offset is still planar (Rz(theta_1) is the left-most DH factor) and
+    takes the 2-D kernel; results follow the reference algorithm for that robot."""
+    from inversekinematicsann_b200.kinematics.inverse import FabrikInverseKinematics
+    from oracle import c_oracle
+    dh = [[0, np.pi / 3, 0.2, -0.1], [2, 0, 0, 0], [0.5, 2, 2, 2], [np.pi / 2, 0, 0, 0]]
+    limits = {'x': [0, 6], 'y': [-6, 6], 'z': [-3, 6]}
+    rng = np.random.RandomState(21)
+    xyz = rng.rand(20_000, 3) * [5, 10, 8] + [0.5, -5, -2.5]
+    ikp = FabrikInverseKinematics(dh, [2, 2, 2, 2], limits)
+    angles, iters = ikp.ikine(xyz, as_array=True, return_iterations=True)
+    want = c_oracle.fabrik_ikine(xyz, dh=np.array(dh, dtype=np.float64))
+    ok = (want["status"] == 0) & np.isfinite(want["angles"]).all(axis=1)
+    assert np.array_equal(iters[ok], want["iters"][ok])
+    assert np.abs(angles[ok] - want["angles"][ok]).max() <= TOL_F64_MODE
+
+
+def test_non_planar_robot_takes_the_generic_kernel():
+    """Twists on joints 2..4 move the seed chain out of the vertical plane: the 3-D kernel (IEEE fp64, reference
+    operation order) serves ikine, with the same flags and statistics."""
+    from inversekinematicsann_b200.kinematics.inverse import FabrikInverseKinematics
+    from inversekinematicsann_b200.robot.robot import OutOfRobotReachException
+    from oracle import c_oracle
+    dh = [[0, np.pi / 2, 0.3, -0.2], [2, 0.1, 0, 0], [0, 2, 2, 2], [np.pi / 2, 0.4, -0.3, 0.2]]
+    limits = {'x': [0, 6], 'y': [-6, 6], 'z': [-3, 6]}
+    rng = np.random.RandomState(22)
+    xyz = rng.rand(10_000, 3) * [5, 10, 8] + [0.5, -5, -2.5]
+    ikg = FabrikInverseKinematics(dh, [2, 2, 2, 2], limits)
+    angles, iters = ikg.ikine(xyz, as_array=True, return_iterations=True)
+    want = c_oracle.fabrik_ikine(xyz, dh=np.array(dh, dtype=np.float64))
+    ok = (want["status"] == 0) & np.isfinite(want["angles"]).all(axis=1)
+    assert ok.mean() > 0.9
+    assert np.array_equal(iters[ok], want["iters"][ok])
+    assert np.abs(angles[ok] - want["angles"][ok]).max() <= 1e-8
+    assert ikg.last_stats.n_solved == len(xyz) and ikg.last_stats.sum_iterations == int(iters.sum())
+    with pytest.raises(OutOfRobotReachException):
+        ikg.ikine([[1, 2, 3], [1, 2, 7]])
