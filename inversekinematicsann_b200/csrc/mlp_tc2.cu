@@ -57,6 +57,7 @@ struct Tc2Net {
     const float *w_first;    // [3][hp]
     const float *b_hidden;   // [1 + n_mma_layers][hp]
     const float *out_scale;  // [n_mma_layers]  1 / (weight scale * X_SCALE)
+    int bias_in_mma;         // hidden width < padded width: feature `hmax` is a constant 1 and the biases are a weight row
     const float *w_last;     // [hp][4]
     float b_last[4];
     double mean_x[3], scale_x[3];
@@ -150,22 +151,29 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32])
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
-// tanh(x) = sign(x) (1 - e) / (1 + e), e = 2^(-2 |x| log2 e): exactly two MUFU ops (ex2, rcp) and no range
-// fix-ups (e is in (0, 1], 1 + e in (1, 2]); absolute error ~1e-7
-__device__ __forceinline__ float fast_tanh(float x)
-{
-#ifdef IKB_TS_ACCURATE_TANH
-    return tanhf(x);
-#endif
-    float e, r;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-2.8853900817779268f * fabsf(x)));
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
-    return copysignf((1.0f - e) * r, x);
-}
-
 __device__ __host__ __forceinline__ int swz_off(int row, int k)  // [rows x 64] fp16 K-major tile, 128B swizzle
 {
     return row * 128 + ((((k >> 3) ^ (row & 7)) & 7) << 4) + ((k & 7) << 1);
+}
+
+// tanh with the accumulator scale folded into the exponent and X_SCALE folded into the result:
+// returns X_SCALE * tanh(v) for v = acc * oscale given t = |acc| * (-2 log2(e) oscale); 2 MUFU + 5 ALU ops
+__device__ __forceinline__ float tanh_scaled(float t, float sign_src)
+{
+    float e, r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(t));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+    return copysignf(fmaf(e, -X_SCALE, X_SCALE) * r, sign_src);
+}
+
+// (hi, lo) fp16 split of two values that already carry the X_SCALE factor
+__device__ __forceinline__ void split_pair_scaled(float s0, float s1, uint32_t &hi, uint32_t &lo)
+{
+    const __half2 h = __floats2half2_rn(s0, s1);
+    const float2 hf = __half22float2(h);
+    const __half2 l = __floats2half2_rn(s0 - hf.x, s1 - hf.y);
+    hi = *reinterpret_cast<const uint32_t *>(&h);
+    lo = *reinterpret_cast<const uint32_t *>(&l);
 }
 
 // y -> (hi, lo) fp16 split of X_SCALE * y, two consecutive features packed per 32-bit word (even feature low)
@@ -212,10 +220,11 @@ __device__ __forceinline__ void first_layer_half(const EpiCtx &cx, int f0, int n
                 y[u] = tanhf(fmaf(cx.in2, __ldg(net.w_first + 2 * cx.HP + f),
                                   fmaf(cx.in1, __ldg(net.w_first + cx.HP + f),
                                        fmaf(cx.in0, __ldg(net.w_first + f), __ldg(net.b_hidden + f)))));
-                if (last_hidden) {
+                if (last_hidden) {  // single hidden layer: same X_SCALE convention as the MMA layers' output sums
                     const float4 w = __ldg(reinterpret_cast<const float4 *>(net.w_last) + f);
-                    out_acc[0] = fmaf(y[u], w.x, out_acc[0]); out_acc[1] = fmaf(y[u], w.y, out_acc[1]);
-                    out_acc[2] = fmaf(y[u], w.z, out_acc[2]); out_acc[3] = fmaf(y[u], w.w, out_acc[3]);
+                    const float ys = y[u] * X_SCALE;
+                    out_acc[0] = fmaf(ys, w.x, out_acc[0]); out_acc[1] = fmaf(ys, w.y, out_acc[1]);
+                    out_acc[2] = fmaf(ys, w.z, out_acc[2]); out_acc[3] = fmaf(ys, w.w, out_acc[3]);
                 }
             }
             split_pair(y[0], y[1], hi[t], lo[t]);
@@ -255,21 +264,30 @@ __device__ __forceinline__ void finish_half(const EpiCtx &cx, uint32_t (&d)[QMAX
                                             float oscale, const float *bias, float (&out_acc)[4])
 {
     const Tc2Net &net = *cx.net;
+    const float cexp = -2.8853900817779268f * oscale;
     auto convert = [&](int q) {
 #pragma unroll
         for (int t = 0; t < 16; ++t) {
             const int f = fbase + q * 32 * CW + 2 * t;
-            const float y0 = fast_tanh(fmaf(__uint_as_float(d[q][2 * t]), oscale, __ldg(bias + f)));
-            const float y1 = fast_tanh(fmaf(__uint_as_float(d[q][2 * t + 1]), oscale, __ldg(bias + f + 1)));
-            if (last_hidden) {
+            const float a0 = __uint_as_float(d[q][2 * t]), a1 = __uint_as_float(d[q][2 * t + 1]);
+            float s0, s1;  // X_SCALE * tanh(pre-activation)
+            if (net.bias_in_mma) {  // the bias row already sits in the accumulator
+                s0 = tanh_scaled(fabsf(a0) * cexp, a0);
+                s1 = tanh_scaled(fabsf(a1) * cexp, a1);
+            } else {
+                const float v0 = fmaf(a0, oscale, __ldg(bias + f)), v1 = fmaf(a1, oscale, __ldg(bias + f + 1));
+                s0 = tanh_scaled(fabsf(v0) * -2.8853900817779268f, v0);
+                s1 = tanh_scaled(fabsf(v1) * -2.8853900817779268f, v1);
+            }
+            if (last_hidden) {  // out_acc carries the X_SCALE factor, removed once at the end
                 const float4 w0 = __ldg(reinterpret_cast<const float4 *>(net.w_last) + f);
                 const float4 w1 = __ldg(reinterpret_cast<const float4 *>(net.w_last) + f + 1);
-                out_acc[0] = fmaf(y1, w1.x, fmaf(y0, w0.x, out_acc[0]));
-                out_acc[1] = fmaf(y1, w1.y, fmaf(y0, w0.y, out_acc[1]));
-                out_acc[2] = fmaf(y1, w1.z, fmaf(y0, w0.z, out_acc[2]));
-                out_acc[3] = fmaf(y1, w1.w, fmaf(y0, w0.w, out_acc[3]));
+                out_acc[0] = fmaf(s1, w1.x, fmaf(s0, w0.x, out_acc[0]));
+                out_acc[1] = fmaf(s1, w1.y, fmaf(s0, w0.y, out_acc[1]));
+                out_acc[2] = fmaf(s1, w1.z, fmaf(s0, w0.z, out_acc[2]));
+                out_acc[3] = fmaf(s1, w1.w, fmaf(s0, w0.w, out_acc[3]));
             } else {
-                split_pair(y0, y1, d[q][2 * t], d[q][2 * t + 1]);
+                split_pair_scaled(s0, s1, d[q][2 * t], d[q][2 * t + 1]);
             }
         }
     };
@@ -535,7 +553,8 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_tc2_kernel(const Tc2Args a)
             }
             if (ch == 0 && row0 + row < a.n) {
                 const float4 other = *reinterpret_cast<const float4 *>(s_io + row * 4);
-                float yv[4] = {out_acc[0] + other.x, out_acc[1] + other.y, out_acc[2] + other.z, out_acc[3] + other.w};
+                float yv[4] = {(out_acc[0] + other.x) * (1.0f / X_SCALE), (out_acc[1] + other.y) * (1.0f / X_SCALE),
+                               (out_acc[2] + other.z) * (1.0f / X_SCALE), (out_acc[3] + other.w) * (1.0f / X_SCALE)};
 #pragma unroll
                 for (int o = 0; o < 4; ++o) {
                     yv[o] += net.b_last[o];
@@ -613,14 +632,32 @@ int ikb_mlp_tc2_pack(IkbMlpTc2 &t, int n_layers, const int *dims, const float *c
     for (int k = 0; k < 3; ++k)
         for (int f = 0; f < dims[1]; ++f)
             wfirst[(size_t)k * hp + f] = weights[0][(size_t)k * dims[1] + f];
+    // When the padded width has a spare column, feature `hmax` is kept at a constant 1 (its own weight makes the
+    // pre-activation 20, tanh(20) == 1.0f) and every layer's biases ride along as weight row `hmax`: the MMA adds
+    // them for free and the epilogue needs no per-element bias loads.
+    const int bias_row = (hp > hmax && NM > 0) ? hmax : -1;
+    constexpr float kConstPre = 20.0f;
     for (int l = 0; l < nh; ++l)
         for (int f = 0; f < dims[l + 1]; ++f)
-            bias[(size_t)l * hp + f] = biases[l][f];
+            bias[(size_t)l * hp + f] = (bias_row >= 0 && l > 0) ? 0.f : biases[l][f];
+    if (bias_row >= 0)
+        bias[bias_row] = kConstPre;  // layer 1 (CUDA cores) produces the constant feature through its bias
+    auto weight_at = [&](int l, int k, int f) -> float {  // true (unscaled) weight of MMA layer l at (k, f)
+        const int fin = dims[l], fout = dims[l + 1];
+        if (k < fin && f < fout)
+            return weights[l][(size_t)k * fout + f];
+        if (k == bias_row)
+            return f < fout ? biases[l][f] : (f == bias_row ? kConstPre : 0.f);
+        return 0.f;
+    };
     for (int m = 0; m < NM; ++m) {
         const int l = m + 1, fin = dims[l], fout = dims[l + 1];
-        float wmax = 0.f;
+        float wmax = bias_row >= 0 ? kConstPre : 0.f;
         for (size_t i = 0; i < (size_t)fin * fout; ++i)
             wmax = std::fmax(wmax, std::fabs(weights[l][i]));
+        if (bias_row >= 0)
+            for (int f = 0; f < fout; ++f)
+                wmax = std::fmax(wmax, std::fabs(biases[l][f]));
         int e = 0;
         if (wmax > 0.f)
             e = 12 - (int)std::ceil(std::log2(wmax));  // largest weight near 2^12: w_lo stays normal, sums stay small
@@ -635,7 +672,7 @@ int ikb_mlp_tc2_pack(IkbMlpTc2 &t, int n_layers, const int *dims, const float *c
                 for (int r = 0; r < nfeat; ++r)
                     for (int c = 0; c < 64; ++c) {
                         const int f = nhalf * 256 + r, k = kc * 64 + c;
-                        const float w = (f < fout && k < fin) ? weights[l][(size_t)k * fout + f] * sw : 0.f;
+                        const float w = weight_at(l, k, f) * sw;
                         const __half h = __float2half_rn(w);
                         const int o = swz_off(r, c) / 2;
                         hi[o] = h;
@@ -657,6 +694,7 @@ int ikb_mlp_tc2_pack(IkbMlpTc2 &t, int n_layers, const int *dims, const float *c
     memset(&n, 0, sizeof n);
     n.n_mma_layers = NM;
     n.hp = hp;
+    n.bias_in_mma = bias_row >= 0 ? 1 : 0;
     n.w_tiles = reinterpret_cast<const __half *>((char *)t.arena + o_tiles);
     n.w_first = reinterpret_cast<const float *>((char *)t.arena + o_first);
     n.b_hidden = reinterpret_cast<const float *>((char *)t.arena + o_bias);
