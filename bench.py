@@ -175,6 +175,24 @@ def main():
     from inversekinematicsann_b200.robot.robot import SixDOFRobot as R
     from inversekinematicsann_b200.sharding import reduce_stats
 
+    def bind_to_gpu_numa_node(index):
+        """Pin this rank to the CPUs next to its GPU so that its pinned staging buffers are allocated on the
+        local NUMA node (eight ranks otherwise share one node's memory controllers for all H2D/D2H traffic)."""
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+            words = (os.cpu_count() + 63) // 64
+            mask = pynvml.nvmlDeviceGetCpuAffinity(handle, words)
+            cpus = {64 * w + b for w, m in enumerate(mask) for b in range(64) if (m >> b) & 1}
+            cpus &= os.sched_getaffinity(0)
+            if cpus:
+                os.sched_setaffinity(0, cpus)
+            return len(cpus)
+        except Exception:
+            return 0
+
+    numa_cpus = bind_to_gpu_numa_node(local_rank) if world > 1 else 0
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
@@ -259,6 +277,14 @@ def main():
         "traffic": traffic,
     }
 
+    # opt-in fp32 iterate (the north star's FP32-pipe variant; outside the parity bar)
+    secs32, _, _ = timed_device_loop(lambda: eng.fabrik_solve_device(xyz, angles, precision="f32"), max(2, args.steps // 2), 3)
+    peak_fp32_k1 = eng.microbench_fma("f32")
+    f32_mode = {"value": n * world * max(2, args.steps // 2) / secs32, "unit": UNIT,
+                "fp32_frac": flops_per_launch / (secs32 / max(2, args.steps // 2)) / 1e12 / peak_fp32_k1,
+                "peak_fp32_tflops": peak_fp32_k1,
+                "note": "fp32 iterate + fp64 angle extraction; ~0.3 % of rows leave the 1e-4 rad band (tests/test_gpu_fabrik.py)"}
+    eng.fabrik_solve_device(xyz, angles)  # restore the fp64 result for the FK error below
     # FK position error of the solved angles (K3), once, outside the timed loop
     err = torch.empty(n, device=dev, dtype=torch.float32)
     eng.stats_reset_torch()
@@ -420,9 +446,11 @@ def main():
                        "output": "float32 [n,4]", "fabrik_precision": "fp64 iterate + fp64 angle extraction",
                        "mean_iterations": total.sum_iterations / (n * world),
                        "iteration_capped_fraction": total.n_iter_capped / (n * world),
-                       "sharding": f"contiguous ranges, {world} rank(s), no data-path collective"},
+                       "sharding": f"contiguous ranges, {world} rank(s), no data-path collective",
+                       "rank_cpu_affinity": numa_cpus or "unchanged"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(gpu_launches), "roofline": roofline,
-            "cpu_baseline": cpu_baseline, "fk_error": fk_error, "fabrik_interior_box": interior, "ann": ann_block,
+            "cpu_baseline": cpu_baseline, "fk_error": fk_error, "fabrik_interior_box": interior,
+            "fabrik_f32_mode": f32_mode, "ann": ann_block,
             "other_configs": extras,
         }
         print(json.dumps(line), flush=True)
