@@ -337,11 +337,11 @@ def main():
     # ---- ANN (config 2) -------------------------------------------------------------------------------
     ann_block = None
     if not args.skip_ann:
-        from oracle import np_oracle  # synthetic weights only (the shipped .h5 is absent from the mount)
-        W, b = np_oracle.synthetic_mlp()
+        from inversekinematicsann_b200 import models  # synthetic weights (the shipped .h5 is absent) + shipped scalers
+        W, b = models.synthetic_weights()
         ann = AnnInverseKinematics(R.dh_matrix, R.links_lengths, R.effector_workspace_limits, device=local_rank)
-        ann.ann.set_model(W, b, np_oracle.SHIPPED_MEAN_X, np_oracle.SHIPPED_SCALE_X,
-                          np_oracle.SHIPPED_MEAN_Y, np_oracle.SHIPPED_SCALE_Y)
+        ann.ann.set_model(W, b, models.SHIPPED_MEAN_X, models.SHIPPED_SCALE_X, models.SHIPPED_MEAN_Y,
+                          models.SHIPPED_SCALE_Y)
         aeng = ann.ann._ensure_uploaded()
         an = args.ann_rows
         axyz = device_points(an, WORKSPACE_BOX, 4321 + rank)

@@ -83,3 +83,16 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in text.replace("no oracle", ""), os.path.join(dirpath, f)
+
+
+def test_product_and_oracle_synthetic_weights_agree():
+    """bench.py's GPU arm takes its synthetic network from the product package, the checker from oracle/; they are
+    independent restatements of the same seeded construction."""
+    from inversekinematicsann_b200 import models
+    from oracle import np_oracle
+    Wp, bp = models.synthetic_weights(seed=5)
+    Wo, bo = np_oracle.synthetic_mlp(seed=5)
+    assert all(np.array_equal(a, b) for a, b in zip(Wp, Wo)) and all(np.array_equal(a, b) for a, b in zip(bp, bo))
+    for name in ("SHIPPED_MEAN_X", "SHIPPED_SCALE_X", "SHIPPED_MEAN_Y", "SHIPPED_SCALE_Y"):
+        assert np.array_equal(getattr(models, name), getattr(np_oracle, name))
+    assert models.REFERENCE_LAYER_DIMS == np_oracle.LAYER_DIMS
