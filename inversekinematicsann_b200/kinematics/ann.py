@@ -5,7 +5,7 @@
 (ann.py:78-85): ``<name>.h5`` plus ``<name>_scaler_x.bin`` / ``<name>_scaler_y.bin`` (joblib
 pickles of sklearn StandardScaler).  Keras/TensorFlow and h5py are optional: when h5py is missing
 the Dense kernels are read from the flat sibling ``<name>.npz`` (keys W0.., b0..) that ``save_model``
-writes and ``tools/h5_to_npz.py`` produces.  Training (ann.py:27-68) is out of scope.
+writes and ``tools/h5_to_npz.py`` produces.  ``train_model`` (ann.py:27-68) lives in training.py.
 """
 import os
 from datetime import datetime
@@ -123,8 +123,17 @@ class ANN:
         dump(self.y_data_skaler, f'{prefix}_{stamp}_scaler_y.bin', compress=True)
         return f'{prefix}_{stamp}'
 
-    def train_model(self, epochs, samples, features):
-        raise NotImplementedError('training (reference ann.py:27-68) is outside the accelerated hot path')
+    def train_model(self, epochs, samples, features, **fit_options):
+        """Train the Sequential model on (positions, joint angles) -- reference ann.py:40-68; see
+        kinematics/training.py for the recipe and the extra `fit_options` (batch_size, learning_rate, device...)."""
+        from . import training
+        x_train, y_train, x_test, y_test, self.x_data_skaler, self.y_data_skaler = \
+            training.fit_training_data(samples, features)
+        kernels, biases, self.history = training.train_dense_stack(x_train, y_train, x_test, y_test, epochs,
+                                                                   **fit_options)
+        self.model = DenseStack(kernels, biases)
+        self._uploaded = False
+        return self.model
 
     def _ensure_uploaded(self):
         if self.model is None:
