@@ -338,10 +338,19 @@ def main():
     ann_block = None
     if not args.skip_ann:
         from inversekinematicsann_b200 import models  # synthetic weights (the shipped .h5 is absent) + shipped scalers
-        W, b = models.synthetic_weights()
         ann = AnnInverseKinematics(R.dh_matrix, R.links_lengths, R.effector_workspace_limits, device=local_rank)
-        ann.ann.set_model(W, b, models.SHIPPED_MEAN_X, models.SHIPPED_SCALE_X, models.SHIPPED_MEAN_Y,
-                          models.SHIPPED_SCALE_Y)
+        trained = os.path.join(os.path.dirname(os.path.abspath(__file__)), "models", "roboarm_b200_r01")
+        if os.path.exists(trained + ".npz"):
+            ann.load_model(trained + ".h5")    # reference file convention (ann.py:78-85); weights come from the .npz
+            weights_note = ("models/roboarm_b200_r01: the reference architecture trained by tools/train_fabrik_model.py "
+                            "on FABRIK-labelled targets (the reference's own .h5 is missing from its tree, so parity "
+                            "with Keras stays unpinned)")
+        else:
+            W, b = models.synthetic_weights()
+            ann.ann.set_model(W, b, models.SHIPPED_MEAN_X, models.SHIPPED_SCALE_X, models.SHIPPED_MEAN_Y,
+                              models.SHIPPED_SCALE_Y)
+            weights_note = "synthetic seeded Glorot (no trained model under models/; parity unpinned)"
+        W, b = ann.ann.model.kernels, ann.ann.model.biases
         aeng = ann.ann._ensure_uploaded()
         an = args.ann_rows
         axyz = device_points(an, WORKSPACE_BOX, 4321 + rank)
@@ -366,6 +375,22 @@ def main():
         ae2e = max_over_ranks(time.perf_counter() - t0)
         peak_fp32 = aeng.microbench_fma("f32")
         tc_s = modes["fp16x3_ts"]
+        # FK round trip of the predictions (BASELINE metric: mean FK position error), on the rows FABRIK can reach
+        aeng.ann_solve_device(axyz, aout, mode="fp16x3_ts")
+        a_err = torch.empty(an, device=dev, dtype=torch.float32)
+        aeng.fk_device(aout, targets=axyz, err=a_err)
+        f_ang = torch.empty(an, 4, device=dev, dtype=torch.float32)
+        f_it = torch.empty(an, device=dev, dtype=torch.int32)
+        f_err = torch.empty(an, device=dev, dtype=torch.float32)
+        eng.fabrik_solve_device(axyz, f_ang, iters=f_it)
+        eng.fk_device(f_ang, targets=axyz, err=f_err)
+        reach = (f_it < 100) & (f_err <= 1e-2)
+        ann_fk = {"rows_reachable": int(reach.sum()), "ann_mean": float(a_err[reach].double().mean()),
+                  "ann_median": float(a_err[reach].median()), "fabrik_mean_same_rows": float(f_err[reach].double().mean()),
+                  "angle_abs_diff_vs_fabrik_mean": float((aout[reach] - f_ang[reach]).abs().double().mean()),
+                  "note": "rows of the workspace sample that FABRIK solves to <= 1e-2 (the population the model was "
+                          "trained on)"}
+        del a_err, f_ang, f_it, f_err
         # executed tensor-core work: 3 partial products (x_hi w_hi, x_lo w_hi, x_hi w_lo) on the 512-padded layers
         hp = 128 * ((max(aeng.mlp_dims[1:-1]) + 127) // 128)
         executed = 3 * 2.0 * hp * hp * (len(aeng.mlp_dims) - 3) * an
@@ -373,7 +398,7 @@ def main():
             "metric": "IK solves/sec (ANN 3->12x500 tanh->4, fused scaler+MLP+scaler)", "value": an * world / tc_s,
             "unit": UNIT, "rows_per_gpu": an, "ms_per_step": tc_s * 1e3, "dtype": "f16x2-split inputs, f32 accumulate",
             "mode": "IKB_MLP_FP16X3_TS: tcgen05 kind::f16, hi/lo split of activations and weights, x_hi as TMEM A operand, fp32 accumulators in TMEM",
-            "weights": "synthetic seeded Glorot (shipped roboarm_model .h5 is missing from the reference mount; parity unpinned)",
+            "weights": weights_note, "fk_error": ann_fk,
             "e2e": {"value": an * world * a_steps / ae2e, "unit": UNIT, "h2d_bytes_per_step": an * 12 * world,
                     "d2h_bytes_per_step": an * 16 * world},
             "roofline": {"kernel": "mlp_tc2_kernel", "bound": "tensor", "achieved": flops / tc_s / 1e12, "peak": bf16_peak,

@@ -57,7 +57,7 @@ struct TcNet {
     const __half *w_tiles;   // [n_mma_layers][NT][KG][hi|lo][128 x 64 swizzled]
     const float *w_first;    // [3][hp] (layer 1 kernel), fp32
     const float *b_hidden;   // [1 + n_mma_layers][hp]
-    const float *inv_sw;     // [n_mma_layers]  1 / (power-of-two weight scale)
+    const float *inv_sw;     // [n_mma_layers]  truncation compensation / (power-of-two weight scale)
     const float *w_last;     // [hp][4]
     float b_last[4];
     double mean_x[3], scale_x[3];
@@ -506,7 +506,9 @@ int ikb_mlp_tc_pack(IkbMlpTc &t, int n_layers, const int *dims, const float *con
             e = 13 - (int)std::ceil(std::log2(wmax));
         e = e > 24 ? 24 : (e < -8 ? -8 : e);
         const float sw = std::ldexp(1.0f, e);
-        isw[m] = 1.0f / sw;
+        // x_hi w_hi and x_hi w_lo share the main accumulator: two truncating steps per K = 16 (mlp.cuh).  Calibration
+        // runs on a trained and a synthetic network put the optimum at 0.8-0.9 of the model's value for this layout.
+        isw[m] = (float)(ikb_tc_truncation_compensation((int)std::lround(0.85 * 2 * ((fin + 15) / 16))) / (double)sw);
         for (int ft = 0; ft < NT; ++ft)
             for (int kc = 0; kc < KG; ++kc) {
                 __half *hi = tiles + (((size_t)(m * NT + ft) * KG + kc) * 2 + 0) * tile_halfs;

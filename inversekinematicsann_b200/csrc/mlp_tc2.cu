@@ -272,8 +272,13 @@ __device__ __forceinline__ void finish_half(const EpiCtx &cx, uint32_t (&d)[QMAX
             const float a0 = __uint_as_float(d[q][2 * t]), a1 = __uint_as_float(d[q][2 * t + 1]);
             float s0, s1;  // X_SCALE * tanh(pre-activation)
             if (net.bias_in_mma) {  // the bias row already sits in the accumulator
+#ifdef IKB_TS_TANH_EXACT  // experiment: libdevice tanhf, to separate the tanh error from the accumulation error
+                s0 = X_SCALE * tanhf(a0 * oscale);
+                s1 = X_SCALE * tanhf(a1 * oscale);
+#else
                 s0 = tanh_scaled(fabsf(a0) * cexp, a0);
                 s1 = tanh_scaled(fabsf(a1) * cexp, a1);
+#endif
             } else {
                 const float v0 = fmaf(a0, oscale, __ldg(bias + f)), v1 = fmaf(a1, oscale, __ldg(bias + f + 1));
                 s0 = tanh_scaled(fabsf(v0) * -2.8853900817779268f, v0);
@@ -663,7 +668,9 @@ int ikb_mlp_tc2_pack(IkbMlpTc2 &t, int n_layers, const int *dims, const float *c
             e = 12 - (int)std::ceil(std::log2(wmax));  // largest weight near 2^12: w_lo stays normal, sums stay small
         e = e > 24 ? 24 : (e < -8 ? -8 : e);
         const float sw = std::ldexp(1.0f, e);
-        oscale[m] = 1.0f / (sw * X_SCALE);
+        // three products per K = 16 step share the accumulator (see ikb_tc_truncation_compensation)
+        const int acc_steps = 3 * ((fin + (bias_row >= 0 ? 1 : 0) + 15) / 16);
+        oscale[m] = (float)(ikb_tc_truncation_compensation(acc_steps) / ((double)sw * X_SCALE));
         for (int nhalf = 0; nhalf < NHALF; ++nhalf)
             for (int kc = 0; kc < KG; ++kc) {
                 __half *hi = tiles + (((size_t)(m * NHALF + nhalf) * KG + kc) * 2 + 0) * tile_halfs;

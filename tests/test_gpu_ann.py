@@ -109,3 +109,60 @@ def test_modes_agree_and_are_deterministic():
         a2 = ann.ikine(xyz, as_array=True).copy()
         assert np.array_equal(a1, a2), mode
         assert np.abs(a1 - s1).max() <= TOL_NORTH_STAR, mode
+
+
+# ---- a TRAINED network (models/roboarm_b200_r01, made by tools/train_fabrik_model.py) --------------------------------
+# Trained weights amplify rounding noise far more than Glorot-initialised ones: two fp32 evaluations of this network
+# that only differ in summation order already disagree by up to 1.7e-5 rad on a few rows in 1e5, so the 1e-5 bar is
+# stated statistically here: every mode must sit at the fp32 noise level (mean, p99) with a bounded tail.
+TRAINED = "models/roboarm_b200_r01"
+
+
+def _trained(mode):
+    import os
+    from inversekinematicsann_b200.kinematics.inverse import AnnInverseKinematics
+    from inversekinematicsann_b200.robot.robot import SixDOFRobot as R
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    ann = AnnInverseKinematics(R.dh_matrix, R.links_lengths, R.effector_workspace_limits)
+    ann.load_model(os.path.join(root, TRAINED + ".h5"))
+    ann.ann.mode = mode
+    return ann
+
+
+def _oracle64(ann, xyz):
+    from oracle import np_oracle
+    a = ann.ann
+    return np_oracle.mlp_predict(xyz, a.model.kernels, a.model.biases, a.x_data_skaler.mean_, a.x_data_skaler.scale_,
+                                 a.y_data_skaler.mean_, a.y_data_skaler.scale_, dtype=np.float64)
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_trained_network_accuracy(mode):
+    ann = _trained(mode)
+    xyz = _points(60_000, seed=21).astype(np.float32)
+    got = ann.ikine(xyz, as_array=True)
+    want = _oracle64(ann, xyz)
+    err = np.abs(got - want).max(axis=1)
+    print(f"[{mode}] trained net vs fp64: mean {np.abs(got - want).mean():.2e} p99 {np.quantile(err, 0.99):.2e} "
+          f"max {err.max():.2e} rows>1e-5 {(err > TOL_NORTH_STAR).sum()}")
+    assert np.abs(got - want).mean() <= 5e-7
+    assert np.quantile(err, 0.99) <= 5e-6
+    assert (err > TOL_NORTH_STAR).mean() <= 2e-3
+    assert err.max() <= (3e-5 if mode == "fp32" else 1.5e-4)
+
+
+def test_accumulator_truncation_compensation_matters(monkeypatch):
+    """tcgen05.mma truncates its fp32 accumulator toward zero at every K = 16 step; csrc/mlp.cuh scales the sums back.
+    Switching the correction off must show the bias (this pins the hardware behaviour the correction is built on)."""
+    xyz = _points(40_000, seed=22).astype(np.float32)
+    on = _trained("fp16x3_ts")
+    want = _oracle64(on, xyz)
+    with_comp = on.ikine(xyz, as_array=True).copy()
+    monkeypatch.setenv("IKB_TC_TRUNC_COMP", "0")
+    off = _trained("fp16x3_ts")          # packs the weights again, now without the correction
+    without = off.ikine(xyz, as_array=True).copy()
+    monkeypatch.delenv("IKB_TC_TRUNC_COMP")
+    on.ann._uploaded = False
+    e_on, e_off = np.abs(with_comp - want).mean(), np.abs(without - want).mean()
+    print(f"mean |dtheta| vs fp64: compensated {e_on:.2e}, uncompensated {e_off:.2e}")
+    assert e_off > 3 * e_on and e_off > 1e-6

@@ -31,6 +31,7 @@ def main():
                     help='drop labels whose FK error exceeds this (unreachable targets and the wrong-branch rows '
                          'of inverse.py:82-85,102-108)')
     ap.add_argument('--seed', type=int, default=1234)
+    ap.add_argument('--patience', type=int, default=12, help='EarlyStopping patience (reference: 12)')
     ap.add_argument('--out', default='gpurun_out/roboarm_b200')
     ap.add_argument('--tf32', action='store_true')
     args = ap.parse_args()
@@ -60,7 +61,8 @@ def main():
     ann = ANN(limits, R.dh_matrix)
     t0 = time.perf_counter()
     ann.train_model(args.epochs, x, y, batch_size=args.batch_size, learning_rate=args.learning_rate,
-                    final_learning_rate=args.final_learning_rate, seed=args.seed, allow_tf32=args.tf32)
+                    final_learning_rate=args.final_learning_rate, seed=args.seed, allow_tf32=args.tf32,
+                    patience=args.patience)
     train_s = time.perf_counter() - t0
 
     os.makedirs(os.path.dirname(args.out) or '.', exist_ok=True)
