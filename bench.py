@@ -298,6 +298,26 @@ def main():
                 "reachable_fraction": float(reach.float().mean().item()),
                 "fk_rows_per_s": n * world * 3 / fk_secs,
                 "fk_hbm_frac": n * 32 * 3 / fk_secs / 1e9 / hbm_peak}
+    # the same error as part of the solve call (ikb_fabrik_solve_device with fk_err_out): above 2^18 rows that is
+    # K1 + K3 on one stream (the fused epilogue measured 2.2 ms extra at 100 M rows against 0.8 ms for K3), below it
+    # K1's fused epilogue (one launch)
+    fused_steps = max(2, args.steps // 2)
+    fused_secs, _, _ = timed_device_loop(lambda: eng.fabrik_solve_device(xyz, angles, fk_err=err), fused_steps, 1)
+    eng.stats_reset_torch()
+    eng.fabrik_solve_device(xyz, angles, fk_err=err)
+    fused_stats = reduce_stats(eng.stats_fetch_torch())
+    small = 100_000
+    s_xyz, s_ang, s_err = xyz[:small].contiguous(), angles[:small].contiguous(), err[:small].contiguous()
+    s_plain, _, _ = timed_device_loop(lambda: eng.fabrik_solve_device(s_xyz, s_ang), 20, 3)
+    s_fused, _, _ = timed_device_loop(lambda: eng.fabrik_solve_device(s_xyz, s_ang, fk_err=s_err), 20, 3)
+    s_two, _, _ = timed_device_loop(lambda: (eng.fabrik_solve_device(s_xyz, s_ang),
+                                             eng.fk_device(s_ang, targets=s_xyz, err=s_err)), 20, 3)
+    fk_error["in_solve_call"] = {"ms_per_step": fused_secs / fused_steps * 1e3, "mean_all": fused_stats.mean_fk_error,
+                                 "extra_ms_vs_plain_solve": (fused_secs / fused_steps - secs / args.steps) * 1e3,
+                                 "separate_fk_kernel_ms": fk_secs / 3 * 1e3,
+                                 "small_batch_100k_us": {"plain": s_plain / 20 * 1e6, "fused_epilogue": s_fused / 20 * 1e6,
+                                                         "two_launches": s_two / 20 * 1e6}}
+    del s_xyz, s_ang, s_err
 
     # interior (fully reachable) box, secondary figure
     xyz_r = device_points(min(n, 50_000_000), INTERIOR_BOX, 99 + rank)
@@ -376,9 +396,10 @@ def main():
         peak_fp32 = aeng.microbench_fma("f32")
         tc_s = modes["fp16x3_ts"]
         # FK round trip of the predictions (BASELINE metric: mean FK position error), on the rows FABRIK can reach
-        aeng.ann_solve_device(axyz, aout, mode="fp16x3_ts")
         a_err = torch.empty(an, device=dev, dtype=torch.float32)
-        aeng.fk_device(aout, targets=axyz, err=a_err)
+        aeng.ann_solve_device(axyz, aout, mode="fp16x3_ts", fk_err=a_err)   # error from the kernel's own output stage
+        fused_a_secs, _, _ = timed_device_loop(
+            lambda: aeng.ann_solve_device(axyz, aout, mode="fp16x3_ts", fk_err=a_err), a_steps, 1)
         f_ang = torch.empty(an, 4, device=dev, dtype=torch.float32)
         f_it = torch.empty(an, device=dev, dtype=torch.int32)
         f_err = torch.empty(an, device=dev, dtype=torch.float32)
@@ -388,8 +409,9 @@ def main():
         ann_fk = {"rows_reachable": int(reach.sum()), "ann_mean": float(a_err[reach].double().mean()),
                   "ann_median": float(a_err[reach].median()), "fabrik_mean_same_rows": float(f_err[reach].double().mean()),
                   "angle_abs_diff_vs_fabrik_mean": float((aout[reach] - f_ang[reach]).abs().double().mean()),
+                  "fused_ms_per_step": fused_a_secs / a_steps * 1e3,
                   "note": "rows of the workspace sample that FABRIK solves to <= 1e-2 (the population the model was "
-                          "trained on)"}
+                          "trained on); errors come from the ANN kernel's fused FK epilogue"}
         del a_err, f_ang, f_it, f_err
         # executed tensor-core work: 3 partial products (x_hi w_hi, x_lo w_hi, x_hi w_lo) on the 512-padded layers
         hp = 128 * ((max(aeng.mlp_dims[1:-1]) + 127) // 128)

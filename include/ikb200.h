@@ -106,12 +106,19 @@ int ikb_check_limits_host(ikb_engine *e, const void *xyz, int xyz_dtype, int64_t
 
 /* ---- FABRIK ikine (inverse.py:115-139 = check_limits + per-target Fabrik.calculate
  *      (fabrik.py:44-67) + __get_angles (inverse.py:54-112)) ----------------------------------- */
+/* fk_err_out (nullable, n values of angles_dtype) = ||FK(angles_out) - target|| per row, the check the reference
+ * CLI draws (cli.py:56-61) -- part of the same call: fused into the solver's epilogue for batches up to 2^18 rows
+ * (one launch), an fk_kernel launch on the same stream above that (measured cheaper there) and for DH tables
+ * without the closed-form FK; fk_stats != 0 accumulates ikb_stats.sum_fk_error / n_fk_error even without the
+ * per-row array. */
 int ikb_fabrik_solve_device(ikb_engine *e, const void *xyz, int xyz_dtype, int64_t n,
                             void *angles_out, int angles_dtype,
-                            int32_t *iters_out /* nullable */, int precision, void *stream);
+                            int32_t *iters_out /* nullable */, void *fk_err_out /* nullable */, int fk_stats,
+                            int precision, void *stream);
 int ikb_fabrik_solve_host(ikb_engine *e, const void *xyz, int xyz_dtype, int64_t n,
                           void *angles_out, int angles_dtype,
-                          int32_t *iters_out /* nullable */, int precision, ikb_stats *stats);
+                          int32_t *iters_out /* nullable */, void *fk_err_out /* nullable */, int fk_stats,
+                          int precision, ikb_stats *stats);
 
 /* ---- Fabrik.calculate with explicit initial chains (fabrik.py:44-67) -------------------------
  * init: n_init x 4 x 3 doubles (n_init == 1 broadcasts one chain to all goals, or n_init == n);
@@ -145,10 +152,12 @@ int ikb_mlp_load(ikb_engine *e, int32_t n_layers, const int32_t *dims,
                  const double mean_y[4], const double scale_y[4]);
 /* replaces AnnInverseKinematics.ikine / ANN.predict (inverse.py:152-155, ann.py:70-76):
  * angles_out is n x 4 float32 (Keras / sklearn return float32). */
+/* fk_err_out / fk_stats as for ikb_fabrik_solve_*: fused into the default IKB_MLP_FP16X3_TS kernel's output stage,
+ * a second launch (fk_kernel) on the same stream for the two cross-check modes. */
 int ikb_ann_solve_device(ikb_engine *e, const void *xyz, int xyz_dtype, int64_t n,
-                         float *angles_out, int mode, void *stream);
+                         float *angles_out, float *fk_err_out /* nullable */, int fk_stats, int mode, void *stream);
 int ikb_ann_solve_host(ikb_engine *e, const void *xyz, int xyz_dtype, int64_t n,
-                       float *angles_out, int mode, ikb_stats *stats);
+                       float *angles_out, float *fk_err_out /* nullable */, int fk_stats, int mode, ikb_stats *stats);
 
 /* ---- trajectory generators (robot/position_generator.py:26-97), written straight into device memory ----
  * kind / params (doubles):

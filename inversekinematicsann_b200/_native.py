@@ -74,16 +74,16 @@ def load():
         "ikb_stats_fetch": (i32, [engine, vp, stats_p]),
         "ikb_check_limits_device": (i32, [engine, vp, i32, i64, vp]),
         "ikb_check_limits_host": (i32, [engine, vp, i32, i64, ctypes.POINTER(i64)]),
-        "ikb_fabrik_solve_device": (i32, [engine, vp, i32, i64, vp, i32, vp, i32, vp]),
-        "ikb_fabrik_solve_host": (i32, [engine, vp, i32, i64, vp, i32, vp, i32, stats_p]),
+        "ikb_fabrik_solve_device": (i32, [engine, vp, i32, i64, vp, i32, vp, vp, i32, i32, vp]),
+        "ikb_fabrik_solve_host": (i32, [engine, vp, i32, i64, vp, i32, vp, vp, i32, i32, stats_p]),
         "ikb_fabrik_calculate_host": (i32, [engine, vp, i64, vp, i64, vp, vp, stats_p]),
         "ikb_fk_device": (i32, [engine, vp, i32, i64, vp, vp, i32, vp, vp]),
         "ikb_fk_host": (i32, [engine, vp, i32, i64, vp, vp, i32, vp, stats_p]),
         "ikb_fk_chain_host": (i32, [engine, vp, vp, ctypes.POINTER(i32)]),
         "ikb_mlp_load": (i32, [engine, ctypes.c_int32, ctypes.POINTER(ctypes.c_int32),
                                ctypes.POINTER(vp), ctypes.POINTER(vp), vp, vp, vp, vp]),
-        "ikb_ann_solve_device": (i32, [engine, vp, i32, i64, vp, i32, vp]),
-        "ikb_ann_solve_host": (i32, [engine, vp, i32, i64, vp, i32, stats_p]),
+        "ikb_ann_solve_device": (i32, [engine, vp, i32, i64, vp, vp, i32, i32, vp]),
+        "ikb_ann_solve_host": (i32, [engine, vp, i32, i64, vp, vp, i32, i32, stats_p]),
         "ikb_generate_device": (i32, [engine, i32, vp, i32, i64, i64, vp, i32, ctypes.c_uint64, vp]),
         "ikb_microbench_fma": (i32, [engine, i32, ctypes.POINTER(dbl)]),
         "ikb_launch_count": (i64, [engine]),

@@ -13,8 +13,8 @@
 
 // launchers implemented next to their kernels
 cudaError_t ikb_launch_fabrik_planar(const void *xyz, int xyz_f64, long long n, long long index_base,
-                                     void *angles, int angles_f64, int *iters, int precision,
-                                     IkbDeviceStats *stats, unsigned long long *work_counter,
+                                     void *angles, int angles_f64, int *iters, void *fk_err, int fk_stats,
+                                     int precision, IkbDeviceStats *stats, unsigned long long *work_counter,
                                      const IkbRobot &rc, int num_sms, cudaStream_t stream);
 cudaError_t ikb_launch_fabrik_generic(const double *init, long long n_init, const double *goals,
                                       long long n, double *chain_out, int *iters,
@@ -369,27 +369,51 @@ int ikb_check_limits_host(ikb_engine *e, const void *xyz, int xyz_dtype, int64_t
 }
 
 // ---- FABRIK ---------------------------------------------------------------------------------------
+// K1's fused error epilogue uses the closed-form FK (joints 2..4 about parallel axes, alpha inside the guard of
+// forward.py:23-25); any other DH table gets K3 as a second launch.
+// Measured on B200 (100 M rows): the fused epilogue adds 2.2 ms to the 21.2 ms solve (K1 is latency-bound on the
+// fp64 pipe with a tight register budget, and the extra fp32 work competes for its issue slots), K3 as a second launch
+// 0.8 ms (it runs at HBM speed while K1 hardly touches HBM).  So the fusion only pays while it saves a launch:
+// below ~2.6e5 rows.
+constexpr long long kFuseFkMaxRows = 1LL << 18;
+static bool fk_fusable(const IkbRobot &rc, long long rows)
+{
+    bool ok = rc.fk_planar_tail != 0 && rows <= kFuseFkMaxRows;
+    for (int j = 0; j < 4; ++j)
+        ok = ok && !(rc.alpha[j] < -6.283185307179586) && !(rc.alpha[j] > 6.283185307179586);
+    return ok;
+}
+
 int ikb_fabrik_solve_device(ikb_engine *e, const void *xyz, int xyz_dtype, int64_t n, void *angles_out,
-                            int angles_dtype, int32_t *iters_out, int precision, void *stream)
+                            int angles_dtype, int32_t *iters_out, void *fk_err_out, int fk_stats, int precision,
+                            void *stream)
 {
     if (!e || n < 0 || (n > 0 && (!xyz || !angles_out)) || bad_dtype(xyz_dtype) || bad_dtype(angles_dtype) ||
         (precision != IKB_FABRIK_F64 && precision != IKB_FABRIK_F32) || n > 0x7fffffffLL)
         return fail(e, IKB_ERR_INVALID, "ikb_fabrik_solve_device: bad argument (n must be < 2^31 per call)");
     IKB_CUDA(e, cudaSetDevice(e->device));
+    const bool want_fk = n > 0 && (fk_err_out || fk_stats);
+    const bool fuse = want_fk && e->rc.planar && fk_fusable(e->rc, n);
     if (!e->rc.planar)  // general DH table: the seed chain leaves the vertical plane -> 3-D kernel
         IKB_CUDA(e, ikb_launch_fabrik_generic_ikine(xyz, xyz_dtype == IKB_F64, n, 0, angles_out,
                                                     angles_dtype == IKB_F64, iters_out, e->d_stats, e->rc,
                                                     (cudaStream_t)stream));
     else
         IKB_CUDA(e, ikb_launch_fabrik_planar(xyz, xyz_dtype == IKB_F64, n, 0, angles_out, angles_dtype == IKB_F64,
-                                             iters_out, precision, e->d_stats, next_counter(e), e->rc,
-                                             e->num_sms, (cudaStream_t)stream));
+                                             iters_out, fuse ? fk_err_out : nullptr, fuse ? fk_stats : 0, precision,
+                                             e->d_stats, next_counter(e), e->rc, e->num_sms, (cudaStream_t)stream));
+    if (want_fk && !fuse) {  // no closed-form FK for this DH table: K3 as a second launch
+        IKB_CUDA(e, ikb_launch_fk(angles_out, angles_dtype == IKB_F64, n, 0, nullptr, xyz, xyz_dtype == IKB_F64,
+                                  fk_err_out, e->d_stats, e->rc, e->num_sms, (cudaStream_t)stream));
+        e->launches++;
+    }
     e->launches += (n > 0);
     return IKB_OK;
 }
 
 int ikb_fabrik_solve_host(ikb_engine *e, const void *xyz, int xyz_dtype, int64_t n, void *angles_out,
-                          int angles_dtype, int32_t *iters_out, int precision, ikb_stats *stats)
+                          int angles_dtype, int32_t *iters_out, void *fk_err_out, int fk_stats, int precision,
+                          ikb_stats *stats)
 {
     if (!e || n < 0 || (n > 0 && (!xyz || !angles_out)) || bad_dtype(xyz_dtype) || bad_dtype(angles_dtype) ||
         (precision != IKB_FABRIK_F64 && precision != IKB_FABRIK_F32))
@@ -397,11 +421,14 @@ int ikb_fabrik_solve_host(ikb_engine *e, const void *xyz, int xyz_dtype, int64_t
     int rc = host_begin(e, n);
     if (rc)
         return rc;
-    const size_t in_row = 3 * esize(xyz_dtype), out_row = 4 * esize(angles_dtype);
+    const size_t in_row = 3 * esize(xyz_dtype), out_row = 4 * esize(angles_dtype), err_row = esize(angles_dtype);
+    const bool want_fk = fk_err_out || fk_stats;
+    const bool fuse = want_fk && e->rc.planar && fk_fusable(e->rc, n);
     int it = 0;
     for (long long lo = 0; lo < n; lo += kHostChunkRows, ++it) {
         Slot &s = e->slots[it % kSlots];
         const long long m = std::min<long long>(kHostChunkRows, n - lo);
+        void *d_err = fk_err_out ? s.d_in2 : nullptr;  // d_in2 is free here (FK targets only)
         IKB_CUDA(e, cudaMemcpyAsync(s.d_in, (const char *)xyz + lo * in_row, m * in_row, cudaMemcpyHostToDevice, s.stream));
         if (!e->rc.planar)
             IKB_CUDA(e, ikb_launch_fabrik_generic_ikine(s.d_in, xyz_dtype == IKB_F64, m, lo, s.d_out,
@@ -410,11 +437,19 @@ int ikb_fabrik_solve_host(ikb_engine *e, const void *xyz, int xyz_dtype, int64_t
         else
             IKB_CUDA(e, ikb_launch_fabrik_planar(s.d_in, xyz_dtype == IKB_F64, m, lo, s.d_out,
                                                  angles_dtype == IKB_F64, iters_out ? s.d_aux : nullptr,
-                                                 precision, e->d_stats, next_counter(e), e->rc, e->num_sms, s.stream));
+                                                 fuse ? d_err : nullptr, fuse ? fk_stats : 0, precision, e->d_stats,
+                                                 next_counter(e), e->rc, e->num_sms, s.stream));
+        if (want_fk && !fuse) {
+            IKB_CUDA(e, ikb_launch_fk(s.d_out, angles_dtype == IKB_F64, m, lo, nullptr, s.d_in, xyz_dtype == IKB_F64,
+                                      d_err, e->d_stats, e->rc, e->num_sms, s.stream));
+            e->launches++;
+        }
         e->launches++;
         IKB_CUDA(e, cudaMemcpyAsync((char *)angles_out + lo * out_row, s.d_out, m * out_row, cudaMemcpyDeviceToHost, s.stream));
         if (iters_out)
             IKB_CUDA(e, cudaMemcpyAsync(iters_out + lo, s.d_aux, m * sizeof(int), cudaMemcpyDeviceToHost, s.stream));
+        if (fk_err_out)
+            IKB_CUDA(e, cudaMemcpyAsync((char *)fk_err_out + lo * err_row, d_err, m * err_row, cudaMemcpyDeviceToHost, s.stream));
     }
     return host_end(e, stats);
 }
@@ -527,7 +562,7 @@ int ikb_mlp_load(ikb_engine *e, int32_t n_layers, const int32_t *dims, const flo
 }
 
 int ikb_ann_solve_device(ikb_engine *e, const void *xyz, int xyz_dtype, int64_t n, float *angles_out,
-                         int mode, void *stream)
+                         float *fk_err_out, int fk_stats, int mode, void *stream)
 {
     if (!e || n < 0 || (n > 0 && (!xyz || !angles_out)) || bad_dtype(xyz_dtype))
         return fail(e, IKB_ERR_INVALID, "ikb_ann_solve_device: bad argument");
@@ -536,8 +571,8 @@ int ikb_ann_solve_device(ikb_engine *e, const void *xyz, int xyz_dtype, int64_t 
     IKB_CUDA(e, cudaSetDevice(e->device));
     std::string msg;
     int launches = 0;
-    int rc = ikb_mlp_launch(e->mlp, xyz, xyz_dtype == IKB_F64, n, 0, angles_out, mode, e->d_stats, e->rc,
-                            e->num_sms, (cudaStream_t)stream, msg, launches);
+    int rc = ikb_mlp_launch(e->mlp, xyz, xyz_dtype == IKB_F64, n, 0, angles_out, fk_err_out, fk_stats, mode,
+                            e->d_stats, e->rc, e->num_sms, (cudaStream_t)stream, msg, launches);
     e->launches += launches;
     if (rc)
         return fail(e, rc, msg);
@@ -545,7 +580,7 @@ int ikb_ann_solve_device(ikb_engine *e, const void *xyz, int xyz_dtype, int64_t 
 }
 
 int ikb_ann_solve_host(ikb_engine *e, const void *xyz, int xyz_dtype, int64_t n, float *angles_out,
-                       int mode, ikb_stats *stats)
+                       float *fk_err_out, int fk_stats, int mode, ikb_stats *stats)
 {
     if (!e || n < 0 || (n > 0 && (!xyz || !angles_out)) || bad_dtype(xyz_dtype))
         return fail(e, IKB_ERR_INVALID, "ikb_ann_solve_host: bad argument");
@@ -559,15 +594,18 @@ int ikb_ann_solve_host(ikb_engine *e, const void *xyz, int xyz_dtype, int64_t n,
     for (long long lo = 0; lo < n; lo += kHostChunkRows, ++it) {
         Slot &s = e->slots[it % kSlots];
         const long long m = std::min<long long>(kHostChunkRows, n - lo);
+        float *d_err = fk_err_out ? (float *)s.d_in2 : nullptr;
         IKB_CUDA(e, cudaMemcpyAsync(s.d_in, (const char *)xyz + lo * in_row, m * in_row, cudaMemcpyHostToDevice, s.stream));
         std::string msg;
         int launches = 0;
-        rc = ikb_mlp_launch(e->mlp, s.d_in, xyz_dtype == IKB_F64, m, lo, (float *)s.d_out, mode, e->d_stats,
-                            e->rc, e->num_sms, s.stream, msg, launches);
+        rc = ikb_mlp_launch(e->mlp, s.d_in, xyz_dtype == IKB_F64, m, lo, (float *)s.d_out, d_err, fk_stats, mode,
+                            e->d_stats, e->rc, e->num_sms, s.stream, msg, launches);
         e->launches += launches;
         if (rc)
             return fail(e, rc, msg);
         IKB_CUDA(e, cudaMemcpyAsync((char *)angles_out + lo * out_row, s.d_out, m * out_row, cudaMemcpyDeviceToHost, s.stream));
+        if (fk_err_out)
+            IKB_CUDA(e, cudaMemcpyAsync(fk_err_out + lo, d_err, m * sizeof(float), cudaMemcpyDeviceToHost, s.stream));
     }
     return host_end(e, stats);
 }

@@ -16,7 +16,7 @@
 //    3 acos, atan2) runs only when 32 parked chains are available, i.e. always at full warp width.
 //  * Work is handed out in chunks of IKB_FABRIK_CHUNK consecutive targets from a global counter
 //    (persistent warps, no tail imbalance); row i of the output always belongs to row i of the input.
-#include "ikb_common.cuh"
+#include "fk_device.cuh"
 
 #define IKB_FABRIK_CHUNK 256
 #define IKB_FABRIK_WARPS 8
@@ -41,6 +41,8 @@ struct FabrikArgs {
     void *angles;
     int angles_f64;
     int *iters;  // nullable
+    void *fk_err;  // nullable: ||FK(angles) - target|| per row in the angles' dtype (fused K3)
+    int fk_stats;  // accumulate sum_fk_error / n_fk_error even without the per-row array
     IkbDeviceStats *stats;
     unsigned long long *work_counter;
     IkbRobot rc;
@@ -202,8 +204,27 @@ __device__ __forceinline__ double planar_radius(double x, double y, double &ux, 
 
 // Finish one solved chain: derive the effector, lift to 3-D, extract the four angles in fp64 as
 // reference inverse.py:54-112 does, write outputs, raise the per-row flags.
+// Out of line on purpose: the fp32 FK needs ~40 registers of its own, and inlined into the epilogue it pushed the
+// register allocation of the whole kernel (the solve got 10 % slower even with the error switched off).  Scalars
+// only, so nothing of the kernel's parameter block has to be spilled for the call.
+__device__ __noinline__ float fused_fk_error_f32(float t0, float t1, float t2, float t3, float tx, float ty, float tz,
+                                                 float a0, float a1, float a2, float a3, float eps0, float w, float ca,
+                                                 float sa)
+{
+    const float th[4] = {t0, t1, t2, t3};
+    return ikb_fk_error_planar_tail<float>(th, tx, ty, tz, a0, a1, a2, a3, eps0, w, ca, sa);
+}
+__device__ __noinline__ double fused_fk_error_f64(double t0, double t1, double t2, double t3, double tx, double ty,
+                                                  double tz, double a0, double a1, double a2, double a3, double eps0,
+                                                  double w, double ca, double sa)
+{
+    const double th[4] = {t0, t1, t2, t3};
+    return ikb_fk_error_planar_tail<double>(th, tx, ty, tz, a0, a1, a2, a3, eps0, w, ca, sa);
+}
+
+template <bool FUSE_FK>
 __device__ __forceinline__ void fabrik_epilogue(const FabrikArgs &a, int idx, int k, double r1,
-                                                double z1, double r2, double z2)
+                                                double z1, double r2, double z2, double &fk_sum, unsigned &fk_cnt)
 {
     const IkbRobot &rc = a.rc;
     const double PI = 3.141592653589793;
@@ -267,6 +288,27 @@ __device__ __forceinline__ void fabrik_epilogue(const FabrikArgs &a, int idx, in
     ikb_store_angles(a.angles, a.angles_f64, idx, th);
     if (a.iters)
         a.iters[idx] = k;
+    if (FUSE_FK) {  // fused K3: FK of the angles as stored, in the stored precision
+        double err;
+        if (a.angles_f64) {
+            err = fused_fk_error_f64(th[0], th[1], th[2], th[3], x, y, z, rc.a[0], rc.a[1], rc.a[2], rc.a[3], rc.eps[0],
+                                     rc.eps[1] + rc.eps[2] + rc.eps[3], rc.cos_alpha[0], rc.sin_alpha[0]);
+            if (a.fk_err)
+                reinterpret_cast<double *>(a.fk_err)[idx] = err;
+        } else {
+            const float e = fused_fk_error_f32((float)th[0], (float)th[1], (float)th[2], (float)th[3], (float)x, (float)y,
+                                               (float)z, (float)rc.a[0], (float)rc.a[1], (float)rc.a[2], (float)rc.a[3],
+                                               (float)rc.eps[0], (float)(rc.eps[1] + rc.eps[2] + rc.eps[3]),
+                                               (float)rc.cos_alpha[0], (float)rc.sin_alpha[0]);
+            if (a.fk_err)
+                reinterpret_cast<float *>(a.fk_err)[idx] = e;
+            err = (double)e;
+        }
+        if (isfinite(err)) {
+            fk_sum += err;
+            ++fk_cnt;
+        }
+    }
 }
 
 // OUT_Q: parked-chain ring; < 32 entries wait when a pass starts and a pass parks at most 32 per chain slot
@@ -277,6 +319,8 @@ struct WarpQueues {
     int out_idx[OUT_Q];
     int out_k[OUT_Q];  // iterations; bit 30 set when the chain stopped on max_iter, not on the tolerance
     Real out_c[4][OUT_Q];
+    double fk_sum[32];  // per-lane sums of the fused FK error (kept out of the register file)
+    unsigned fk_cnt[32];
 };
 
 #define IKB_CAPPED_BIT 0x40000000
@@ -284,7 +328,7 @@ struct WarpQueues {
 // CHAINS = independent chains per lane.  The pass is one long dependency chain (every instruction
 // needs the previous result), so a second chain per lane doubles the instruction-level parallelism a
 // warp offers the FP64 pipe; its cost is registers (fewer resident warps).
-template <typename Real, int CHAINS>
+template <typename Real, int CHAINS, bool FUSE_FK>
 __global__ void __launch_bounds__(IKB_FABRIK_WARPS * 32, (CHAINS == 1 ? IKB_FABRIK_MIN_CTAS : IKB_FABRIK_MIN_CTAS2))
     fabrik_planar_kernel(const FabrikArgs a)
 {
@@ -296,6 +340,10 @@ __global__ void __launch_bounds__(IKB_FABRIK_WARPS * 32, (CHAINS == 1 ? IKB_FABR
     const int lane = threadIdx.x & 31;
     WarpQueues<Real, OUT_Q> &q = s_queues[threadIdx.x >> 5];
     const unsigned lt = ikb_lanemask_lt();
+    if (FUSE_FK) {
+        q.fk_sum[lane] = 0.0;
+        q.fk_cnt[lane] = 0u;
+    }
     const IkbRobot &rc = a.rc;
     const Real R0 = (Real)rc.seed_r[0], Z0 = (Real)rc.seed_z[0];
     const Real d1 = (Real)rc.links[1], d2 = (Real)rc.links[2];
@@ -439,8 +487,8 @@ __global__ void __launch_bounds__(IKB_FABRIK_WARPS * 32, (CHAINS == 1 ? IKB_FABR
                 int slot = out_head + lane;
                 slot -= slot >= OUT_Q ? OUT_Q : 0;
                 const int k_raw = q.out_k[slot], k_done = k_raw & (IKB_CAPPED_BIT - 1);
-                fabrik_epilogue(a, q.out_idx[slot], k_done, (double)q.out_c[0][slot], (double)q.out_c[1][slot],
-                                (double)q.out_c[2][slot], (double)q.out_c[3][slot]);
+                fabrik_epilogue<FUSE_FK>(a, q.out_idx[slot], k_done, (double)q.out_c[0][slot], (double)q.out_c[1][slot],
+                                (double)q.out_c[2][slot], (double)q.out_c[3][slot], q.fk_sum[lane], q.fk_cnt[lane]);
                 iters_local += (unsigned)k_done;
                 ++solved_local;
                 capped_local += (k_raw & IKB_CAPPED_BIT) ? 1u : 0u;
@@ -461,6 +509,14 @@ __global__ void __launch_bounds__(IKB_FABRIK_WARPS * 32, (CHAINS == 1 ? IKB_FABR
         atomicAdd(&a.stats->n_solved, (unsigned long long)sv);
         if (cp)
             atomicAdd(&a.stats->n_iter_capped, (unsigned long long)cp);
+    }
+    if (FUSE_FK) {
+        const double es = ikb_warp_sum(q.fk_sum[lane]);
+        const unsigned ec = ikb_warp_sum(q.fk_cnt[lane]);
+        if (lane == 0 && ec != 0) {
+            atomicAdd(&a.stats->sum_fk_error, es);
+            atomicAdd(&a.stats->n_fk_error, (unsigned long long)ec);
+        }
     }
 }
 
@@ -651,8 +707,8 @@ __global__ void __launch_bounds__(128) fabrik_generic_ikine_kernel(const FabrikG
 
 // ---- launchers (called from capi.cu) --------------------------------------------------------------
 cudaError_t ikb_launch_fabrik_planar(const void *xyz, int xyz_f64, long long n, long long index_base,
-                                     void *angles, int angles_f64, int *iters, int precision,
-                                     IkbDeviceStats *stats, unsigned long long *work_counter,
+                                     void *angles, int angles_f64, int *iters, void *fk_err, int fk_stats,
+                                     int precision, IkbDeviceStats *stats, unsigned long long *work_counter,
                                      const IkbRobot &rc, int num_sms, cudaStream_t stream)
 {
     if (n <= 0)
@@ -660,6 +716,7 @@ cudaError_t ikb_launch_fabrik_planar(const void *xyz, int xyz_f64, long long n, 
     FabrikArgs a;
     a.xyz = xyz; a.xyz_f64 = xyz_f64; a.n = n; a.index_base = index_base;
     a.angles = angles; a.angles_f64 = angles_f64; a.iters = iters;
+    a.fk_err = fk_err; a.fk_stats = fk_stats;
     a.stats = stats; a.work_counter = work_counter; a.rc = rc;
     cudaError_t err = cudaMemsetAsync(work_counter, 0, sizeof(unsigned long long), stream);
     if (err != cudaSuccess)
@@ -670,10 +727,18 @@ cudaError_t ikb_launch_fabrik_planar(const void *xyz, int xyz_f64, long long n, 
     long long grid = (long long)num_sms * (IKB_FABRIK_CHAINS == 1 ? IKB_FABRIK_MIN_CTAS : IKB_FABRIK_MIN_CTAS2);
     if (want < grid)
         grid = want;
-    if (precision == IKB_FABRIK_F32)
-        fabrik_planar_kernel<float, IKB_FABRIK_CHAINS><<<(unsigned)grid, per_cta, 0, stream>>>(a);
-    else
-        fabrik_planar_kernel<double, IKB_FABRIK_CHAINS><<<(unsigned)grid, per_cta, 0, stream>>>(a);
+    const bool fuse = fk_err != nullptr || fk_stats != 0;  // the caller checked rc.fk_planar_tail
+    if (precision == IKB_FABRIK_F32) {
+        if (fuse)
+            fabrik_planar_kernel<float, IKB_FABRIK_CHAINS, true><<<(unsigned)grid, per_cta, 0, stream>>>(a);
+        else
+            fabrik_planar_kernel<float, IKB_FABRIK_CHAINS, false><<<(unsigned)grid, per_cta, 0, stream>>>(a);
+    } else {
+        if (fuse)
+            fabrik_planar_kernel<double, IKB_FABRIK_CHAINS, true><<<(unsigned)grid, per_cta, 0, stream>>>(a);
+        else
+            fabrik_planar_kernel<double, IKB_FABRIK_CHAINS, false><<<(unsigned)grid, per_cta, 0, stream>>>(a);
+    }
     return cudaGetLastError();
 }
 

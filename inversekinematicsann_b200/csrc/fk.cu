@@ -7,95 +7,9 @@
 // (cli.py:60, inverse.py:130, tests/forward_unit.py:30) and ||pos - target||.  The chain kernel
 // returns all four cumulative 4x4 matrices for the (T, [T1..T4]) return value of fkine.
 // HBM-bound: 16 B angles + 12 B target in, 4 B error out per row (fp32 buffers).
-#include "ikb_common.cuh"
+#include "fk_device.cuh"
 
 namespace {
-
-// sin/cos for |x| <= 2 pi (larger angles are rejected by the guard of forward.py:23-25 anyway):
-// two-term Cody-Waite reduction by pi/2 (|k| <= 4, exact products) + the cephes single-precision
-// kernels on [-pi/4, pi/4]; max error ~1.2e-7.  libdevice's sincosf carries a Payne-Hanek slow path whose
-// integer instructions made the fp32 FK kernel instruction-bound instead of HBM-bound.
-__device__ __forceinline__ void ikb_sincos(float x, float *s, float *c)
-{
-    const float k = rintf(x * 0.63661977236758134f);
-    float r = fmaf(k, -1.57079625129699707031f, x);
-    r = fmaf(k, -7.54978941586159635335e-8f, r);
-    const int q = (int)k;
-    const float r2 = r * r;
-    float sp = fmaf(r2, -1.9515295891e-4f, 8.3321608736e-3f);
-    sp = fmaf(sp, r2, -1.6666654611e-1f);
-    sp = fmaf(sp * r2, r, r);
-    float cp = fmaf(r2, 2.443315711809948e-5f, -1.388731625493765e-3f);
-    cp = fmaf(cp, r2, 4.166664568298827e-2f);
-    cp = fmaf(cp * r2, r2, fmaf(r2, -0.5f, 1.0f));
-    const float ss = (q & 1) ? cp : sp, cc = (q & 1) ? sp : cp;
-    *s = (q & 2) ? -ss : ss;
-    *c = ((q + 1) & 2) ? -cc : cc;
-}
-__device__ __forceinline__ void ikb_sincos(double x, double *s, double *c) { sincos(x, s, c); }
-
-// Position-only DH chain.  General form: p += R [a c, a s, eps]; R = R Rz(theta) Rx(alpha).
-// When joints 2..4 have alpha == 0 (rc.fk_planar_tail: every arm of the reference's family, robot.py:40) the
-// tail is planar in joint 1's frame and the product collapses to
-//   local = (sum a_i cos(phi_i), sum a_i sin(phi_i), sum eps_i),  phi_i = theta_2 + .. + theta_i
-//   p     = Rz(theta_1) ([a_1, 0, eps_1] + Rx(alpha_1) local)
-// with the cumulative angles formed by the addition theorems -- ~1/3 of the general path's instructions,
-// which is what lets the fp32 kernel run at HBM speed.
-template <typename Real>
-__device__ __forceinline__ bool fk_position(const IkbRobot &rc, const Real th[4], Real &px, Real &py,
-                                            Real &pz)
-{
-    const Real TWO_PI = (Real)6.283185307179586;
-    bool ok = true;
-    Real s[4], c[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        ok &= !(th[i] < -TWO_PI) & !(th[i] > TWO_PI);  // forward.py:23-25 (NaN passes, as upstream)
-        ikb_sincos(th[i], &s[i], &c[i]);
-    }
-    if (rc.fk_planar_tail) {
-        Real cs = c[1], sn = s[1];
-        Real u = (Real)rc.a[1] * cs, v = (Real)rc.a[1] * sn;
-#pragma unroll
-        for (int i = 2; i < 4; ++i) {
-            const Real cn = cs * c[i] - sn * s[i];
-            sn = sn * c[i] + cs * s[i];
-            cs = cn;
-            u += (Real)rc.a[i] * cs;
-            v += (Real)rc.a[i] * sn;
-        }
-        const Real w = (Real)(rc.eps[1] + rc.eps[2] + rc.eps[3]);
-        const Real ca = (Real)rc.cos_alpha[0], sa = (Real)rc.sin_alpha[0];
-        const Real lx = (Real)rc.a[0] + u, ly = v * ca - w * sa, lz = (Real)rc.eps[0] + v * sa + w * ca;
-        px = c[0] * lx - s[0] * ly;
-        py = s[0] * lx + c[0] * ly;
-        pz = lz;
-        return ok;
-    }
-    Real R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
-    px = py = pz = 0;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const Real a = (Real)rc.a[i], e = (Real)rc.eps[i];
-        const Real vx = a * c[i], vy = a * s[i];
-        px += R[0] * vx + R[1] * vy + R[2] * e;
-        py += R[3] * vx + R[4] * vy + R[5] * e;
-        pz += R[6] * vx + R[7] * vy + R[8] * e;
-        if (i < 3) {
-            const Real ca = (Real)rc.cos_alpha[i], sa = (Real)rc.sin_alpha[i];
-            // M = Rz(t) Rx(alpha) = [[c, -s ca, s sa], [s, c ca, -c sa], [0, sa, ca]]
-            const Real m01 = -s[i] * ca, m02 = s[i] * sa, m11 = c[i] * ca, m12 = -c[i] * sa;
-#pragma unroll
-            for (int r = 0; r < 3; ++r) {
-                const Real r0 = R[3 * r], r1 = R[3 * r + 1], r2 = R[3 * r + 2];
-                R[3 * r] = r0 * c[i] + r1 * s[i];
-                R[3 * r + 1] = r0 * m01 + r1 * m11 + r2 * sa;
-                R[3 * r + 2] = r0 * m02 + r1 * m12 + r2 * ca;
-            }
-        }
-    }
-    return ok;
-}
 
 struct FkArgs {
     const void *angles;

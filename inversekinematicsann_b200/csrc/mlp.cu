@@ -319,40 +319,54 @@ int ikb_mlp_upload(IkbMlp &m, int n_layers, const int *dims, const float *const 
     return IKB_OK;
 }
 
+cudaError_t ikb_launch_fk(const void *angles, int angles_f64, long long n, long long index_base,
+                          void *pos_out, const void *targets, int xyz_f64, void *err_out,
+                          IkbDeviceStats *stats, const IkbRobot &rc, int num_sms, cudaStream_t stream);
+
 int ikb_mlp_launch(const IkbMlp &m, const void *xyz, int xyz_f64, long long n, long long index_base,
-                   float *angles_out, int mode, IkbDeviceStats *stats, const IkbRobot &rc, int num_sms,
-                   cudaStream_t stream, std::string &err, int &launches)
+                   float *angles_out, float *fk_err_out, int fk_stats, int mode, IkbDeviceStats *stats,
+                   const IkbRobot &rc, int num_sms, cudaStream_t stream, std::string &err, int &launches)
 {
     launches = 0;
     if (n <= 0)
         return IKB_OK;
+    if (mode == IKB_MLP_FP16X3_TS) {  // default mode: the FK error is part of the kernel's output stage
+        const int rc_tc = ikb_mlp_tc2_launch(*m.tc2, xyz, xyz_f64, n, index_base, angles_out, fk_err_out, fk_stats,
+                                             stats, rc, num_sms, stream, err);
+        launches = rc_tc == IKB_OK ? 1 : 0;
+        return rc_tc;
+    }
     if (mode == IKB_MLP_FP16X3_TC) {
         const int rc_tc = ikb_mlp_tc_launch(*m.tc, xyz, xyz_f64, n, index_base, angles_out, stats, rc, num_sms,
                                             stream, err);
-        launches = rc_tc == IKB_OK ? 1 : 0;
-        return rc_tc;
-    }
-    if (mode == IKB_MLP_FP16X3_TS) {
-        const int rc_tc = ikb_mlp_tc2_launch(*m.tc2, xyz, xyz_f64, n, index_base, angles_out, stats, rc, num_sms,
-                                             stream, err);
-        launches = rc_tc == IKB_OK ? 1 : 0;
-        return rc_tc;
-    }
-    if (mode != IKB_MLP_FP32_SIMT) {
+        if (rc_tc != IKB_OK)
+            return rc_tc;
+        launches = 1;
+    } else if (mode == IKB_MLP_FP32_SIMT) {
+        MlpArgs a;
+        a.xyz = xyz; a.xyz_f64 = xyz_f64; a.n = n; a.index_base = index_base; a.out = angles_out;
+        a.stats = stats; a.rc = rc; a.net = m.dev;
+        const long long tiles = (n + TM - 1) / TM;
+        const unsigned grid = (unsigned)(tiles < num_sms ? tiles : num_sms);
+        mlp_simt_kernel<<<grid, THREADS, SMEM_TOTAL, stream>>>(a);
+        cudaError_t ce = cudaGetLastError();
+        if (ce != cudaSuccess) {
+            err = std::string("mlp_simt_kernel launch: ") + cudaGetErrorString(ce);
+            return IKB_ERR_CUDA;
+        }
+        launches = 1;
+    } else {
         err = "ikb_ann_solve: unknown MLP mode";
         return IKB_ERR_INVALID;
     }
-    MlpArgs a;
-    a.xyz = xyz; a.xyz_f64 = xyz_f64; a.n = n; a.index_base = index_base; a.out = angles_out;
-    a.stats = stats; a.rc = rc; a.net = m.dev;
-    const long long tiles = (n + TM - 1) / TM;
-    const unsigned grid = (unsigned)(tiles < num_sms ? tiles : num_sms);
-    mlp_simt_kernel<<<grid, THREADS, SMEM_TOTAL, stream>>>(a);
-    cudaError_t ce = cudaGetLastError();
-    if (ce != cudaSuccess) {
-        err = std::string("mlp_simt_kernel launch: ") + cudaGetErrorString(ce);
-        return IKB_ERR_CUDA;
+    if (fk_err_out || fk_stats) {  // the cross-check modes run K3 as a second launch on the same stream
+        cudaError_t ce = ikb_launch_fk(angles_out, 0, n, index_base, nullptr, xyz, xyz_f64, fk_err_out, stats, rc,
+                                       num_sms, stream);
+        if (ce != cudaSuccess) {
+            err = std::string("fk_kernel launch: ") + cudaGetErrorString(ce);
+            return IKB_ERR_CUDA;
+        }
+        ++launches;
     }
-    launches = 1;
     return IKB_OK;
 }

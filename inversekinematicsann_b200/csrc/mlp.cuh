@@ -55,7 +55,7 @@ int ikb_mlp_tc2_pack(IkbMlpTc2 &t, int n_layers, const int *dims, const float *c
                      const float *const *biases, const double mean_x[3], const double scale_x[3],
                      const double mean_y[4], const double scale_y[4], std::string &err);
 int ikb_mlp_tc2_launch(const IkbMlpTc2 &t, const void *xyz, int xyz_f64, long long n, long long index_base,
-                       float *angles_out, IkbDeviceStats *stats, const IkbRobot &rc, int num_sms,
+                       float *angles_out, float *fk_err_out, int fk_stats, IkbDeviceStats *stats, const IkbRobot &rc, int num_sms,
                        cudaStream_t stream, std::string &err);
 
 struct IkbMlp {
@@ -73,5 +73,5 @@ int ikb_mlp_upload(IkbMlp &m, int n_layers, const int *dims, const float *const 
                    const double mean_y[4], const double scale_y[4], std::string &err);
 void ikb_mlp_free(IkbMlp &m);
 int ikb_mlp_launch(const IkbMlp &m, const void *xyz, int xyz_f64, long long n, long long index_base,
-                   float *angles_out, int mode, IkbDeviceStats *stats, const IkbRobot &rc, int num_sms,
+                   float *angles_out, float *fk_err_out, int fk_stats, int mode, IkbDeviceStats *stats, const IkbRobot &rc, int num_sms,
                    cudaStream_t stream, std::string &err, int &launches);

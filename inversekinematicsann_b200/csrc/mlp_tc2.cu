@@ -22,6 +22,7 @@
 #include <cstring>
 #include <vector>
 
+#include "fk_device.cuh"
 #include "mlp.cuh"
 
 #ifdef IKB_TC_DEBUG
@@ -70,6 +71,8 @@ struct Tc2Args {
     long long n;
     long long index_base;
     float *out;
+    float *fk_err;  // nullable: ||FK(out) - target|| per row (fused K3)
+    int fk_stats;   // accumulate sum_fk_error / n_fk_error even without the per-row array
     IkbDeviceStats *stats;
     IkbRobot rc;
     Tc2Net net;
@@ -187,6 +190,28 @@ __device__ __forceinline__ void split_pair(float y0, float y1, uint32_t &hi, uin
     const __half2 l = __floats2half2_rn(s0 - hf.x, s1 - hf.y);
     hi = *reinterpret_cast<const uint32_t *>(&h);
     lo = *reinterpret_cast<const uint32_t *>(&l);
+}
+
+// Fused K3: ||FK(angles) - target|| for the row this thread just produced, same arithmetic as
+// fk.cu on the same fp32 angles; one warp-level sum and one atomic pair per warp and tile.
+__device__ __forceinline__ void fused_fk_error(const Tc2Args &a, long long i, bool live, const float (&th)[4])
+{
+    float err = 0.f;
+    bool counted = false;
+    if (live) {
+        double x, y, z;
+        ikb_load_xyz(a.xyz, a.xyz_f64, i, x, y, z);
+        err = ikb_fk_error<float>(a.rc, th, (float)x, (float)y, (float)z);
+        if (a.fk_err)
+            a.fk_err[i] = err;
+        counted = isfinite(err);
+    }
+    const float part = ikb_warp_sum(counted ? err : 0.f);
+    const unsigned cnt = __popc(__ballot_sync(IKB_FULL_MASK, counted));
+    if ((threadIdx.x & 31) == 0 && cnt) {
+        atomicAdd(&a.stats->sum_fk_error, (double)part);
+        atomicAdd(&a.stats->n_fk_error, (unsigned long long)cnt);
+    }
 }
 
 // Everything an epilogue thread needs to turn pre-activations into the next layer's operands.
@@ -556,7 +581,8 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_tc2_kernel(const Tc2Args a)
                 }
                 asm volatile("bar.sync 1, %0;" ::"n"(N_EPI_WARPS * 32));
             }
-            if (ch == 0 && row0 + row < a.n) {
+            if (ch == 0) {
+                const bool live = row0 + row < a.n;
                 const float4 other = *reinterpret_cast<const float4 *>(s_io + row * 4);
                 float yv[4] = {(out_acc[0] + other.x) * (1.0f / X_SCALE), (out_acc[1] + other.y) * (1.0f / X_SCALE),
                                (out_acc[2] + other.z) * (1.0f / X_SCALE), (out_acc[3] + other.w) * (1.0f / X_SCALE)};
@@ -566,7 +592,10 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_tc2_kernel(const Tc2Args a)
                     yv[o] = __fmul_rn(yv[o], net.scale_y[o]);
                     yv[o] = __fadd_rn(yv[o], net.mean_y[o]);
                 }
-                reinterpret_cast<float4 *>(a.out)[row0 + row] = make_float4(yv[0], yv[1], yv[2], yv[3]);
+                if (live)
+                    reinterpret_cast<float4 *>(a.out)[row0 + row] = make_float4(yv[0], yv[1], yv[2], yv[3]);
+                if (a.fk_err || a.fk_stats)  // the ch == 0 threads are four whole warps: warp-uniform branch
+                    fused_fk_error(a, row0 + row, live, yv);
             }
             asm volatile("bar.sync 1, %0;" ::"n"(N_EPI_WARPS * 32));
         }
@@ -726,8 +755,8 @@ int ikb_mlp_tc2_pack(IkbMlpTc2 &t, int n_layers, const int *dims, const float *c
 }
 
 int ikb_mlp_tc2_launch(const IkbMlpTc2 &t, const void *xyz, int xyz_f64, long long n, long long index_base,
-                       float *angles_out, IkbDeviceStats *stats, const IkbRobot &rc, int num_sms,
-                       cudaStream_t stream, std::string &err)
+                       float *angles_out, float *fk_err_out, int fk_stats, IkbDeviceStats *stats,
+                       const IkbRobot &rc, int num_sms, cudaStream_t stream, std::string &err)
 {
     if (!t.usable) {
         err = "IKB_MLP_FP16X3_TS: this network cannot use the tensor-core path (" + t.why + ")";
@@ -735,6 +764,7 @@ int ikb_mlp_tc2_launch(const IkbMlpTc2 &t, const void *xyz, int xyz_f64, long lo
     }
     Tc2Args a;
     a.xyz = xyz; a.xyz_f64 = xyz_f64; a.n = n; a.index_base = index_base; a.out = angles_out;
+    a.fk_err = fk_err_out; a.fk_stats = fk_stats;
     a.stats = stats; a.rc = rc; a.net = t.net;
     const long long tiles = (n + ROWS - 1) / ROWS;
     const unsigned grid = (unsigned)(tiles < num_sms ? tiles : num_sms);

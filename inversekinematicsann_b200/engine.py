@@ -153,20 +153,29 @@ class IkEngine:
                                                     xyz.shape[0], ctypes.byref(first)), "ikb_check_limits_host")
         return int(first.value)
 
-    def fabrik_solve(self, xyz, out=None, out_dtype=np.float64, precision="f64", return_iters=False):
-        """reference inverse.py:115-139 on an (n, 3) array.  Returns (angles[n,4], stats[, iters])."""
+    def fabrik_solve(self, xyz, out=None, out_dtype=np.float64, precision="f64", return_iters=False,
+                     return_fk_error=False, fk_stats=False):
+        """reference inverse.py:115-139 on an (n, 3) array.  Returns (angles[n,4], stats[, iters][, fk_error]);
+        `return_fk_error` adds ||FK(angles) - target|| per row from the solver's own epilogue (no second pass),
+        `fk_stats` only its sum / count in `stats`."""
         xyz = self._rows(xyz, 3, "points")
         n = xyz.shape[0]
         if out is None:
             out = np.empty((n, 4), dtype=out_dtype)
         iters = np.empty(n, dtype=np.int32) if return_iters else None
+        fk_err = np.empty(n, dtype=out.dtype) if return_fk_error else None
         s = _native.IkbStats()
         prec = {"f64": _native.IKB_FABRIK_F64, "f32": _native.IKB_FABRIK_F32}[precision]
         self._check(self._lib.ikb_fabrik_solve_host(
             self._handle, xyz.ctypes.data, _np_dtype_code(xyz), n, out.ctypes.data, _np_dtype_code(out),
-            iters.ctypes.data if return_iters else None, prec, ctypes.byref(s)), "ikb_fabrik_solve_host")
-        st = IkStats.from_c(s)
-        return (out, st, iters) if return_iters else (out, st)
+            iters.ctypes.data if return_iters else None, fk_err.ctypes.data if return_fk_error else None,
+            int(bool(fk_stats)), prec, ctypes.byref(s)), "ikb_fabrik_solve_host")
+        res = (out, IkStats.from_c(s))
+        if return_iters:
+            res += (iters,)
+        if return_fk_error:
+            res += (fk_err,)
+        return res
 
     def fabrik_calculate(self, init, goals):
         """reference fabrik.py:44-67 for explicit initial chains.  init: (4,3) or (n,4,3); goals (n,3)."""
@@ -236,17 +245,19 @@ class IkEngine:
         self.mlp_dims = dims
         self.mlp_macs_per_row = int(sum(a * b for a, b in zip(dims[:-1], dims[1:])))
 
-    def ann_solve(self, xyz, out=None, mode="fp32"):
-        """reference ann.py:70-76 on an (n, 3) array -> (angles float32 [n,4], stats)."""
+    def ann_solve(self, xyz, out=None, mode="fp32", return_fk_error=False, fk_stats=False):
+        """reference ann.py:70-76 on an (n, 3) array -> (angles float32 [n,4], stats[, fk_error float32 [n]])."""
         xyz = self._rows(xyz, 3, "points")
         n = xyz.shape[0]
         if out is None:
             out = np.empty((n, 4), dtype=np.float32)
+        fk_err = np.empty(n, dtype=np.float32) if return_fk_error else None
         s = _native.IkbStats()
         self._check(self._lib.ikb_ann_solve_host(self._handle, xyz.ctypes.data, _np_dtype_code(xyz), n,
-                                                 out.ctypes.data, _MLP_MODES[mode], ctypes.byref(s)),
+                                                 out.ctypes.data, fk_err.ctypes.data if return_fk_error else None,
+                                                 int(bool(fk_stats)), _MLP_MODES[mode], ctypes.byref(s)),
                     "ikb_ann_solve_host")
-        return out, IkStats.from_c(s)
+        return (out, IkStats.from_c(s), fk_err) if return_fk_error else (out, IkStats.from_c(s))
 
     def microbench_fma(self, dtype="f64"):
         out = ctypes.c_double(0.0)
@@ -264,20 +275,26 @@ class IkEngine:
             raise ValueError(f"{what} must be a contiguous (n, {cols}) tensor")
         return t
 
-    def fabrik_solve_device(self, xyz, out, iters=None, precision="f64"):
+    def fabrik_solve_device(self, xyz, out, iters=None, precision="f64", fk_err=None, fk_stats=False):
         xyz = self._dev_rows(xyz, 3, "points")
         out = self._dev_rows(out, 4, "angles")
+        if fk_err is not None and (fk_err.dtype != out.dtype or fk_err.numel() != out.shape[0]):
+            raise ValueError("fk_err must have the angles' dtype and one value per row")
         prec = {"f64": _native.IKB_FABRIK_F64, "f32": _native.IKB_FABRIK_F32}[precision]
         self._check(self._lib.ikb_fabrik_solve_device(
             self._handle, xyz.data_ptr(), _torch_dtype_code(xyz), xyz.shape[0], out.data_ptr(),
-            _torch_dtype_code(out), iters.data_ptr() if iters is not None else None, prec,
+            _torch_dtype_code(out), iters.data_ptr() if iters is not None else None,
+            fk_err.data_ptr() if fk_err is not None else None, int(bool(fk_stats)), prec,
             _torch_stream_ptr(self.device)), "ikb_fabrik_solve_device")
 
-    def ann_solve_device(self, xyz, out, mode="fp32"):
+    def ann_solve_device(self, xyz, out, mode="fp32", fk_err=None, fk_stats=False):
         xyz = self._dev_rows(xyz, 3, "points")
         out = self._dev_rows(out, 4, "angles")
+        if fk_err is not None and (str(fk_err.dtype) != "torch.float32" or fk_err.numel() != out.shape[0]):
+            raise ValueError("fk_err must be float32 with one value per row")
         self._check(self._lib.ikb_ann_solve_device(
             self._handle, xyz.data_ptr(), _torch_dtype_code(xyz), xyz.shape[0], out.data_ptr(),
+            fk_err.data_ptr() if fk_err is not None else None, int(bool(fk_stats)),
             _MLP_MODES[mode], _torch_stream_ptr(self.device)), "ikb_ann_solve_device")
 
     def fk_device(self, angles, targets=None, pos=None, err=None):

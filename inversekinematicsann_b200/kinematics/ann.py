@@ -146,12 +146,13 @@ class ANN:
             self._uploaded = True
         return eng
 
-    def predict_with_stats(self, position, out=None):
+    def predict_with_stats(self, position, out=None, return_fk_error=False):
         eng = self._ensure_uploaded()
         arr = np.asarray(position)
         if arr.dtype not in (np.float32, np.float64):
             arr = arr.astype(np.float64)
-        return eng.ann_solve(arr.reshape(-1, 3), out=out, mode=self.mode)
+        return eng.ann_solve(arr.reshape(-1, 3), out=out, mode=self.mode, return_fk_error=return_fk_error,
+                             fk_stats=return_fk_error)
 
     def predict(self, position):
         """Predict joint angles: (n, 4) float32 ndarray like Keras + sklearn return (ann.py:70-76).

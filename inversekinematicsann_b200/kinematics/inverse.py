@@ -82,23 +82,27 @@ class FabrikInverseKinematics(InverseKinematics):
         self.precision = precision
         self.last_stats = None
 
-    def ikine(self, dest_points, as_array=False, return_iterations=False, out=None):
+    def ikine(self, dest_points, as_array=False, return_iterations=False, out=None, return_fk_error=False):
         """Joint angles [theta1..theta4] for every destination point.
 
         `out` (optional, implies as_array): a preallocated (n, 4) float32/float64 array -- e.g. pinned
-        host memory -- that receives the angles."""
+        host memory -- that receives the angles.  `return_fk_error` appends ||FK(angles) - point|| per point (the
+        check the reference CLI plots, cli.py:56-61), computed inside the solver kernel."""
         arr = points_to_array(dest_points)
         if arr.shape[0] == 0:
-            return np.zeros((0, 4)) if as_array else []
+            empty = np.zeros((0, 4)) if as_array else []
+            extras = ((np.zeros(0, np.int32),) if return_iterations else ()) + \
+                     ((np.zeros(0),) if return_fk_error else ())
+            return (empty,) + extras if extras else empty
         if out is not None:
             as_array = True
-        res = self._engine().fabrik_solve(arr, out=out, precision=self.precision,
-                                          return_iters=return_iterations)
+        res = self._engine().fabrik_solve(arr, out=out, precision=self.precision, return_iters=return_iterations,
+                                          return_fk_error=return_fk_error, fk_stats=return_fk_error)
         angles, stats = res[0], res[1]
         self.last_stats = stats
         self._raise_from_stats(dest_points, stats)
         out = angles if as_array else angles.tolist()
-        return (out, res[2]) if return_iterations else out
+        return (out,) + tuple(res[2:]) if len(res) > 2 else out
 
 
 class AnnInverseKinematics(InverseKinematics):
@@ -113,14 +117,17 @@ class AnnInverseKinematics(InverseKinematics):
         """Load model weights + scalers (reference inverse.py:148-150)."""
         self.ann.load_model(model_name)
 
-    def ikine(self, dest_points, as_array=False, out=None):
+    def ikine(self, dest_points, as_array=False, out=None, return_fk_error=False):
         """Predict thetas using the neural network (limits checked first, inverse.py:154)."""
         arr = points_to_array(dest_points)
         if arr.shape[0] == 0:
-            return np.zeros((0, 4), dtype=np.float32) if as_array else []
+            empty = np.zeros((0, 4), dtype=np.float32) if as_array else []
+            return (empty, np.zeros(0, np.float32)) if return_fk_error else empty
         if out is not None:
             as_array = True
-        angles, stats = self.ann.predict_with_stats(arr, out=out)
+        res = self.ann.predict_with_stats(arr, out=out, return_fk_error=return_fk_error)
+        angles, stats = res[0], res[1]
         self.last_stats = stats
         self._raise_from_stats(dest_points, stats)
-        return angles if as_array else angles.tolist()
+        angles = angles if as_array else angles.tolist()
+        return (angles, res[2]) if return_fk_error else angles

@@ -72,3 +72,88 @@ def test_general_dh_table_matches_oracle():
     _, chain = fk.fkine(list(ang[0]))
     _, want_chain = c_oracle.fk_chain(ang[0], dh=np.array(dh, dtype=np.float64))
     np.testing.assert_allclose(np.array(chain), want_chain, rtol=0, atol=1e-12)
+
+
+# ---- FK error fused into the solvers' epilogues ---------------------------------------------------
+def _robot():
+    from inversekinematicsann_b200.robot.robot import SixDOFRobot as R
+    return R
+
+
+@pytest.mark.parametrize("n", [50_001, 300_000])  # below / above the row count where K1 fuses the error (capi.cu)
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_fabrik_fused_fk_error_equals_k3(dtype, n):
+    from inversekinematicsann_b200.kinematics.forward import ForwardKinematics
+    from inversekinematicsann_b200.kinematics.inverse import FabrikInverseKinematics
+    R = _robot()
+    rng = np.random.default_rng(8)
+    pts = rng.uniform([0, -6, -3], [6, 6, 6], size=(n, 3)).astype(dtype)
+    ik = FabrikInverseKinematics(R.dh_matrix, R.links_lengths, R.effector_workspace_limits)
+    out = np.empty((pts.shape[0], 4), dtype=dtype)
+    angles, fused = ik.ikine(pts, out=out, return_fk_error=True)
+    assert fused.dtype == dtype and fused.shape == (pts.shape[0],)
+    _, separate = ForwardKinematics(R.dh_matrix).fkine_positions(angles, targets=pts)
+    tol = 2e-6 if dtype == np.float32 else 1e-12
+    assert np.abs(fused - separate).max() <= tol
+    assert abs(ik.last_stats.mean_fk_error - float(np.mean(separate, dtype=np.float64))) <= 1e-6
+    # the same angles as without the fused error
+    assert np.array_equal(angles, ik.ikine(pts, as_array=True).astype(dtype))
+
+
+def test_fabrik_fused_fk_error_vs_oracle():
+    from inversekinematicsann_b200.kinematics.inverse import FabrikInverseKinematics
+    from oracle import c_oracle
+    R = _robot()
+    rng = np.random.default_rng(9)
+    pts = rng.uniform([0, -6, -3], [6, 6, 6], size=(20_000, 3))
+    ik = FabrikInverseKinematics(R.dh_matrix, R.links_lengths, R.effector_workspace_limits)
+    angles, it, err = ik.ikine(pts, as_array=True, return_iterations=True, return_fk_error=True)
+    want = c_oracle.fabrik_ikine(pts)
+    _, _, want_err = c_oracle.fk_positions(want["angles"], targets=pts)
+    assert np.array_equal(it, want["iters"])
+    # the wrong-branch rows of inverse.py:82-85,102-108 reproduce too: errors match row by row
+    assert np.abs(err - want_err).max() <= 2e-3 and np.abs(err - want_err).mean() <= 1e-6
+
+
+@pytest.mark.parametrize("mode", ["fp16x3_ts", "fp16x3", "fp32"])
+def test_ann_fused_fk_error_equals_k3(mode):
+    from inversekinematicsann_b200.kinematics.forward import ForwardKinematics
+    from inversekinematicsann_b200.kinematics.inverse import AnnInverseKinematics
+    from oracle import np_oracle
+    R = _robot()
+    W, b = np_oracle.synthetic_mlp(seed=3, dims=[3, 500, 500, 4])
+    ann = AnnInverseKinematics(R.dh_matrix, R.links_lengths, R.effector_workspace_limits)
+    ann.ann.mode = mode
+    ann.ann.set_model(W, b, np_oracle.SHIPPED_MEAN_X, np_oracle.SHIPPED_SCALE_X, np_oracle.SHIPPED_MEAN_Y,
+                      np_oracle.SHIPPED_SCALE_Y)
+    rng = np.random.default_rng(10)
+    for n in (1, 127, 128, 129, 40_003):
+        pts = rng.uniform([0, -6, -3], [6, 6, 6], size=(n, 3)).astype(np.float32)
+        angles, fused = ann.ikine(pts, as_array=True, return_fk_error=True)
+        _, separate = ForwardKinematics(R.dh_matrix).fkine_positions(angles, targets=pts)
+        assert fused.dtype == np.float32 and np.abs(fused - separate).max() <= 2e-6, (mode, n)
+        assert abs(ann.last_stats.mean_fk_error - float(np.mean(separate, dtype=np.float64))) <= 1e-6
+        assert np.array_equal(angles, ann.ikine(pts, as_array=True))
+
+
+def test_device_entry_points_fk_stats_only():
+    import torch
+    from inversekinematicsann_b200.kinematics._shared import get_engine
+    eng = get_engine()
+    g = torch.Generator(device="cuda").manual_seed(4)
+    xyz = torch.rand(200_000, 3, device="cuda", generator=g) * torch.tensor([6.0, 12.0, 9.0], device="cuda") + \
+        torch.tensor([0.0, -6.0, -3.0], device="cuda")
+    ang = torch.empty(xyz.shape[0], 4, device="cuda")
+    err = torch.empty(xyz.shape[0], device="cuda")
+    eng.stats_reset_torch()
+    eng.fabrik_solve_device(xyz, ang, fk_stats=True)
+    only_stats = eng.stats_fetch_torch()
+    eng.stats_reset_torch()
+    eng.fabrik_solve_device(xyz, ang, fk_err=err)
+    with_rows = eng.stats_fetch_torch()
+    assert only_stats.n_fk_error == with_rows.n_fk_error == xyz.shape[0]
+    assert abs(only_stats.mean_fk_error - with_rows.mean_fk_error) <= 1e-9
+    assert abs(with_rows.mean_fk_error - float(err.double().mean())) <= 1e-6
+    eng.stats_reset_torch()
+    eng.fabrik_solve_device(xyz, ang)
+    assert eng.stats_fetch_torch().n_fk_error == 0
