@@ -373,9 +373,9 @@ int ikb_check_limits_host(ikb_engine *e, const void *xyz, int xyz_dtype, int64_t
 // forward.py:23-25); any other DH table gets K3 as a second launch.
 // Measured on B200 (100 M rows): the fused epilogue adds 2.2 ms to the 21.2 ms solve (K1 is latency-bound on the
 // fp64 pipe with a tight register budget, and the extra fp32 work competes for its issue slots), K3 as a second launch
-// 0.8 ms (it runs at HBM speed while K1 hardly touches HBM).  So the fusion only pays while it saves a launch:
-// below ~2.6e5 rows.
-constexpr long long kFuseFkMaxRows = 1LL << 18;
+// 0.8 ms (it runs at HBM speed while K1 hardly touches HBM); at 1e5 rows 21 us against 12 us.  So the fusion only
+// pays while the saved launch dominates: CLI-sized batches.
+constexpr long long kFuseFkMaxRows = 1LL << 14;
 static bool fk_fusable(const IkbRobot &rc, long long rows)
 {
     bool ok = rc.fk_planar_tail != 0 && rows <= kFuseFkMaxRows;
