@@ -41,6 +41,8 @@ def parse_args():
     ap.add_argument("--rows", type=int, default=100_000_000, help="FABRIK targets per GPU (config 3)")
     ap.add_argument("--ann-rows", type=int, default=1_000_000, help="ANN targets per GPU (config 2)")
     ap.add_argument("--e2e-rows", type=int, default=0, help="host-resident rows per GPU for e2e (0 = --rows)")
+    ap.add_argument("--ann-big-rows", type=int, default=125_000_000,
+                    help="ANN targets per GPU for the config-4 leg (1e9 over 8 GPUs); 0 skips it")
     ap.add_argument("--skip-ann", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")
     return ap.parse_args()
@@ -437,6 +439,25 @@ def main():
                           "roofline": {"bound": "fp32", "achieved": flops / modes["fp32"] / 1e12, "peak": peak_fp32,
                                        "unit": "TFLOP/s", "frac": flops / modes["fp32"] / 1e12 / peak_fp32}},
         }
+        # BASELINE config 4: 125 M uniform workspace targets per GPU (1e9 on 8 GPUs), predictions + FK round trip,
+        # the per-GPU (sum, count) reduced across ranks; same kernel, the error comes from its fused epilogue
+        del axyz, aout
+        big = args.ann_big_rows
+        if big > 0:
+            bxyz = device_points(big, WORKSPACE_BOX, 777 + rank)
+            bout = torch.empty(big, 4, device=dev, dtype=torch.float32)
+            aeng.stats_reset_torch()
+            b_secs, _, _ = timed_device_loop(lambda: aeng.ann_solve_device(bxyz, bout, mode="fp16x3_ts", fk_stats=True), 2, 1)
+            b_stats = reduce_stats(aeng.stats_fetch_torch())
+            gpu_launches += 2 * world
+            ann_block["config4_fk_round_trip"] = {
+                "value": big * world * 2 / b_secs, "unit": UNIT, "rows_per_gpu": big, "rows_total": big * world,
+                "ms_per_step": b_secs / 2 * 1e3, "mean_fk_error_all_rows": b_stats.mean_fk_error,
+                "rows_in_error_mean": b_stats.n_fk_error // 3,
+                "roofline_frac": 2.0 * aeng.mlp_macs_per_row * big / (b_secs / 2) / 1e12 / bf16_peak,
+                "note": "uniform over the whole workspace box, 37 % of which FABRIK (and hence the training set) cannot "
+                        "reach, so the all-rows mean is dominated by unreachable targets; see fk_error for reachable rows"}
+            del bxyz, bout
         if rank == 0 and not args.skip_cpu:
             rows = 100_000
             ann_block["cpu_baseline"] = {"value": cpu_ann_rate(rows, W, b), "unit": UNIT, "cores": os.cpu_count(),

@@ -76,16 +76,19 @@ def gather_rows(local_rows, n_total, dst=0):
     return torch.cat(parts, dim=0)
 
 
-class ShardedFabrik:
-    """Drop-in for FabrikInverseKinematics.ikine over all ranks of a torchrun job: every rank passes
-    the SAME full trajectory (as the reference's caller would), solves only its contiguous range on
-    its own GPU, and rank 0 gets the full (n, 4) result; the reference's exceptions are raised on
-    every rank from the reduced diagnostics."""
+class _ShardedIkine:
+    """Every rank passes the SAME full trajectory (as the reference's caller would), solves only its contiguous
+    range on its own GPU, and rank 0 gets the full (n, 4) result; the reference's exceptions are raised on every
+    rank from the reduced diagnostics.  With `fk_error=True` the per-rank error sums are all-reduced as well
+    (BASELINE config 4: the FK round trip of every prediction), available as `ik.last_stats.mean_fk_error`."""
 
     def __init__(self, ik):
         self.ik = ik
 
-    def ikine(self, points, gather=True):
+    def _solve_local(self, eng, local, fk_error):
+        raise NotImplementedError
+
+    def ikine(self, points, gather=True, fk_error=False):
         import numpy as np
         from .kinematics._shared import points_to_array
         arr = points_to_array(points)
@@ -94,8 +97,8 @@ class ShardedFabrik:
         lo, hi = shard_range(arr.shape[0], rank, world)
         local = arr[lo:hi]
         eng = self.ik._engine()
-        angles, stats = eng.fabrik_solve(local, precision=self.ik.precision) if hi > lo else \
-            (np.zeros((0, 4)), IkStats())
+        angles, stats = self._solve_local(eng, local, fk_error) if hi > lo else \
+            (np.zeros((0, 4), dtype=self._out_dtype), IkStats())
         total = reduce_stats(stats, row_offset=lo)
         self.ik.last_stats = total
         self.ik._raise_from_stats(points, total)
@@ -104,3 +107,20 @@ class ShardedFabrik:
         dev = f"cuda:{eng.device}" if dist.get_backend() == "nccl" else "cpu"
         full = gather_rows(torch.from_numpy(angles).to(dev), arr.shape[0])
         return None if full is None else full.cpu().numpy()
+
+
+class ShardedFabrik(_ShardedIkine):
+    """Drop-in for FabrikInverseKinematics.ikine over all ranks of a torchrun job."""
+    _out_dtype = "float64"
+
+    def _solve_local(self, eng, local, fk_error):
+        return eng.fabrik_solve(local, precision=self.ik.precision, fk_stats=fk_error)[:2]
+
+
+class ShardedAnn(_ShardedIkine):
+    """Drop-in for AnnInverseKinematics.ikine over all ranks (weights replicated per GPU at load time)."""
+    _out_dtype = "float32"
+
+    def _solve_local(self, eng, local, fk_error):
+        eng = self.ik.ann._ensure_uploaded()
+        return eng.ann_solve(local, mode=self.ik.ann.mode, fk_stats=fk_error)[:2]

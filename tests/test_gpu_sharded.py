@@ -64,3 +64,36 @@ def test_two_rank_sharded_fabrik(tmp_path):
     for r in range(2):
         msg = open(tmp_path / f"raised{r}.txt").read()
         assert "is out of manipulator reach area" in msg and "6.5" in msg
+
+
+def _ann_worker(rank, world, port, out_dir):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), IKB_DEVICE="0")
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from inversekinematicsann_b200.kinematics.inverse import AnnInverseKinematics
+    from inversekinematicsann_b200.robot.robot import SixDOFRobot as R
+    from inversekinematicsann_b200.sharding import ShardedAnn
+    ann = AnnInverseKinematics(R.dh_matrix, R.links_lengths, R.effector_workspace_limits, device=0)
+    ann.load_model(os.path.join(ROOT, "models", "roboarm_b200_r01.h5"))
+    rng = np.random.RandomState(23)
+    pts = (rng.rand(20_003, 3) * [6, 12, 9] + [0, -6, -3]).astype(np.float32)
+    full = ShardedAnn(ann).ikine(pts, fk_error=True)     # config 4's shape: predictions + reduced FK round trip
+    if rank == 0:
+        np.save(os.path.join(out_dir, "ann.npy"), full)
+        np.save(os.path.join(out_dir, "ann_fk.npy"), np.array([ann.last_stats.sum_fk_error, ann.last_stats.n_fk_error]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_sharded_ann_with_fk_round_trip(tmp_path):
+    from inversekinematicsann_b200.kinematics.inverse import AnnInverseKinematics
+    from inversekinematicsann_b200.robot.robot import SixDOFRobot as R
+    mp.spawn(_ann_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
+    rng = np.random.RandomState(23)
+    pts = (rng.rand(20_003, 3) * [6, 12, 9] + [0, -6, -3]).astype(np.float32)
+    ann = AnnInverseKinematics(R.dh_matrix, R.links_lengths, R.effector_workspace_limits)
+    ann.load_model(os.path.join(ROOT, "models", "roboarm_b200_r01.h5"))
+    single, err = ann.ikine(pts, as_array=True, return_fk_error=True)
+    assert np.array_equal(single, np.load(tmp_path / "ann.npy"))
+    s, c = np.load(tmp_path / "ann_fk.npy")
+    assert c == 20_003 and abs(s / c - float(np.mean(err, dtype=np.float64))) <= 1e-6
