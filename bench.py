@@ -266,7 +266,7 @@ def main():
         if t.get("rows") == n:
             traffic = t.get("dram_bytes_per_launch")
     roofline = {
-        "kernel": "fabrik_planar_kernel<double>", "bound": "fp64",
+        "kernel": "fabrik_split_kernel<double>", "bound": "fp64",
         "achieved": flops_per_launch / launch_s / 1e12, "peak": peak_fp64, "unit": "TFLOP/s",
         "frac": flops_per_launch / launch_s / 1e12 / peak_fp64,
         "peak_source": "measured live: DFMA-chain microbenchmark (ikb_microbench_fma); MEASURED_PEAKS.json has no "
@@ -300,7 +300,7 @@ def main():
                 "reachable_fraction": float(reach.float().mean().item()),
                 "fk_rows_per_s": n * world * 3 / fk_secs,
                 "fk_hbm_frac": n * 32 * 3 / fk_secs / 1e9 / hbm_peak}
-    # the same error as part of the solve call (ikb_fabrik_solve_device with fk_err_out): above 2^14 rows that is
+    # the same error as part of the solve call (ikb_fabrik_solve_device with fk_err_out): above 2^10 rows that is
     # K1 + K3 on one stream (the fused epilogue measured 2.2 ms extra at 100 M rows against 0.8 ms for K3), below it
     # K1's fused epilogue (one launch)
     fused_steps = max(2, args.steps // 2)
@@ -308,7 +308,7 @@ def main():
     eng.stats_reset_torch()
     eng.fabrik_solve_device(xyz, angles, fk_err=err)
     fused_stats = reduce_stats(eng.stats_fetch_torch())
-    small = 4096
+    small = 512
     s_xyz, s_ang, s_err = xyz[:small].contiguous(), angles[:small].contiguous(), err[:small].contiguous()
     s_plain, _, _ = timed_device_loop(lambda: eng.fabrik_solve_device(s_xyz, s_ang), 20, 3)
     s_fused, _, _ = timed_device_loop(lambda: eng.fabrik_solve_device(s_xyz, s_ang, fk_err=s_err), 20, 3)
@@ -317,7 +317,7 @@ def main():
     fk_error["in_solve_call"] = {"ms_per_step": fused_secs / fused_steps * 1e3, "mean_all": fused_stats.mean_fk_error,
                                  "extra_ms_vs_plain_solve": (fused_secs / fused_steps - secs / args.steps) * 1e3,
                                  "separate_fk_kernel_ms": fk_secs / 3 * 1e3,
-                                 "small_batch_4096_us": {"plain": s_plain / 20 * 1e6, "fused_epilogue": s_fused / 20 * 1e6,
+                                 "small_batch_512_us": {"plain": s_plain / 20 * 1e6, "fused_epilogue": s_fused / 20 * 1e6,
                                                          "two_launches": s_two / 20 * 1e6}}
     del s_xyz, s_ang, s_err
 

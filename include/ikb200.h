@@ -107,7 +107,7 @@ int ikb_check_limits_host(ikb_engine *e, const void *xyz, int xyz_dtype, int64_t
 /* ---- FABRIK ikine (inverse.py:115-139 = check_limits + per-target Fabrik.calculate
  *      (fabrik.py:44-67) + __get_angles (inverse.py:54-112)) ----------------------------------- */
 /* fk_err_out (nullable, n values of angles_dtype) = ||FK(angles_out) - target|| per row, the check the reference
- * CLI draws (cli.py:56-61) -- part of the same call: fused into the solver's epilogue for batches up to 2^14 rows
+ * CLI draws (cli.py:56-61) -- part of the same call: fused into the solver's epilogue for batches up to 2^10 rows
  * (one launch), an fk_kernel launch on the same stream above that (measured cheaper there) and for DH tables
  * without the closed-form FK; fk_stats != 0 accumulates ikb_stats.sum_fk_error / n_fk_error even without the
  * per-row array. */

@@ -112,7 +112,7 @@ void to_public(const IkbDeviceStats &d, ikb_stats *o)
 
 unsigned long long *next_counter(ikb_engine *e)
 {
-    unsigned long long *p = e->d_counters + (e->counter_seq % kCounterRing);
+    unsigned long long *p = e->d_counters + 2 * (e->counter_seq % kCounterRing);  // pairs: lane-refill + far kernel
     e->counter_seq++;
     return p;
 }
@@ -225,7 +225,7 @@ int ikb_engine_create(const ikb_config *cfg, ikb_engine **out)
     e->num_sms = prop.multiProcessorCount;
     IKB_CREATE_CUDA(cudaMalloc(&e->d_stats, sizeof(IkbDeviceStats)));
     IKB_CREATE_CUDA(cudaMallocHost(&e->h_stats, sizeof(IkbDeviceStats)));
-    IKB_CREATE_CUDA(cudaMalloc(&e->d_counters, kCounterRing * sizeof(unsigned long long)));
+    IKB_CREATE_CUDA(cudaMalloc(&e->d_counters, 2 * kCounterRing * sizeof(unsigned long long)));
     *e->h_stats = fresh_stats();
     IKB_CREATE_CUDA(cudaMemcpy(e->d_stats, e->h_stats, sizeof(IkbDeviceStats), cudaMemcpyHostToDevice));
 
@@ -373,9 +373,9 @@ int ikb_check_limits_host(ikb_engine *e, const void *xyz, int xyz_dtype, int64_t
 // forward.py:23-25); any other DH table gets K3 as a second launch.
 // Measured on B200 (100 M rows): the fused epilogue adds 2.2 ms to the 21.2 ms solve (K1 is latency-bound on the
 // fp64 pipe with a tight register budget, and the extra fp32 work competes for its issue slots), K3 as a second launch
-// 0.8 ms (it runs at HBM speed while K1 hardly touches HBM); at 1e5 rows 21 us against 12 us.  So the fusion only
-// pays while the saved launch dominates: CLI-sized batches.
-constexpr long long kFuseFkMaxRows = 1LL << 14;
+// 0.8 ms (it runs at HBM speed while K1 hardly touches HBM); at 1e5 rows 21 us against 12 us, at 4096 rows 12 us
+// against 5 us.  So the fusion only pays while the saved launch dominates: CLI-sized batches.
+constexpr long long kFuseFkMaxRows = 1LL << 10;
 static bool fk_fusable(const IkbRobot &rc, long long rows)
 {
     bool ok = rc.fk_planar_tail != 0 && rows <= kFuseFkMaxRows;

@@ -16,6 +16,8 @@
 //    3 acos, atan2) runs only when 32 parked chains are available, i.e. always at full warp width.
 //  * Work is handed out in chunks of IKB_FABRIK_CHUNK consecutive targets from a global counter
 //    (persistent warps, no tail imbalance); row i of the output always belongs to row i of the input.
+#include <cstdlib>
+
 #include "fk_device.cuh"
 
 #define IKB_FABRIK_CHUNK 256
@@ -45,6 +47,8 @@ struct FabrikArgs {
     int fk_stats;  // accumulate sum_fk_error / n_fk_error even without the per-row array
     IkbDeviceStats *stats;
     unsigned long long *work_counter;
+    unsigned long long *work_counter_far;
+    double far_thr2;  // > 0: targets with |T - S|^2 above it belong to fabrik_far_kernel (see is_far)
     IkbRobot rc;
 };
 
@@ -105,7 +109,9 @@ __device__ __forceinline__ bool fabrik_pass(PlanarChain<Real> &c, Real Tr, Real 
     return start_off | goal_band.outside(n2);                            // fabrik.py:63
 }
 
-#define IKB_FABRIK_IDLE_T 4  // lanes allowed to sit idle before the warp leaves its inner loop to refill
+#ifndef IKB_FABRIK_IDLE_T
+#define IKB_FABRIK_IDLE_T 8  // lanes allowed to sit idle before the warp leaves its inner loop to refill
+#endif
 
 // sqrt(x) for x >= 0 through the reciprocal square root (2 ulp); exact 0 for x == 0
 __device__ __forceinline__ double fast_sqrt(double x)
@@ -200,6 +206,25 @@ __device__ __forceinline__ double planar_radius(double x, double y, double &ux, 
     ux = on_axis ? 1.0 : x * rs;
     uy = on_axis ? 0.0 : y * rs;
     return on_axis ? 0.0 : n2 * rs;
+}
+
+// Out-of-reach split.  With |T - S| > d1 + d2 + d3 + tol the goal error |f3 - T| = ||T - f2| - d3| can never get
+// below tol (f2 stays within d1 + d2 of S), so the reference runs exactly max_iter passes on such a target and its
+// last verdict is "not converged".  Those targets -- 38 % of a uniform workspace sample, 87 % of its passes -- go to
+// fabrik_far_kernel, which runs the passes in lockstep without the per-pass verdict, parking and refill; the
+// lane-refill kernel skips them when it stages its input.  Both kernels evaluate this predicate on the raw target,
+// with explicitly rounded operations, so that every row is claimed by exactly one of them.
+__device__ __forceinline__ bool is_far(double x, double y, double z, double R0, double Z0, double thr2)
+{
+    const double q = __fma_rn(x, x, __dmul_rn(y, y)), dz = __dadd_rn(z, -Z0);
+    double d2;
+    if (R0 == 0.0) {  // base on the z axis (every arm of the reference's family): no square root needed
+        d2 = __fma_rn(dz, dz, q);
+    } else {
+        const double dr = __dadd_rn(__dsqrt_rn(q), -R0);
+        d2 = __fma_rn(dr, dr, __dmul_rn(dz, dz));
+    }
+    return (d2 > thr2) & (d2 < 1.0e300);  // false for NaN and for infinite targets (those stop after one pass)
 }
 
 // Finish one solved chain: derive the effector, lift to 3-D, extract the four angles in fp64 as
@@ -329,13 +354,11 @@ struct WarpQueues {
 // needs the previous result), so a second chain per lane doubles the instruction-level parallelism a
 // warp offers the FP64 pipe; its cost is registers (fewer resident warps).
 template <typename Real, int CHAINS, bool FUSE_FK>
-__global__ void __launch_bounds__(IKB_FABRIK_WARPS * 32, (CHAINS == 1 ? IKB_FABRIK_MIN_CTAS : IKB_FABRIK_MIN_CTAS2))
-    fabrik_planar_kernel(const FabrikArgs a)
+__device__ __forceinline__ void fabrik_refill_loop(const FabrikArgs &a, WarpQueues<Real, 32 + 32 * CHAINS> *s_queues)
 {
     // per-warp rings: input queue (pre-staged targets) and output queue (parked solved chains);
     // one struct per warp so every access is "warp base + constant + slot"
     constexpr int OUT_Q = 32 + 32 * CHAINS;
-    __shared__ WarpQueues<Real, OUT_Q> s_queues[IKB_FABRIK_WARPS];
 
     const int lane = threadIdx.x & 31;
     WarpQueues<Real, OUT_Q> &q = s_queues[threadIdx.x >> 5];
@@ -383,15 +406,21 @@ __global__ void __launch_bounds__(IKB_FABRIK_WARPS * 32, (CHAINS == 1 ? IKB_FABR
             }
             if (!exhausted) {
                 const int m = (int)min((long long)32, cur_end - cur);
-                if (lane < m) {
-                    double x, y, z, ux, uy;
+                double x = 0, y = 0, z = 0, ux, uy;
+                bool mine = lane < m;
+                if (mine) {
                     ikb_load_xyz(a.xyz, a.xyz_f64, cur + lane, x, y, z);
-                    const int slot = (in_head + in_cnt + lane) & (IKB_Q - 1);
+                    if (a.far_thr2 > 0.0)
+                        mine = !is_far(x, y, z, rc.seed_r[0], rc.seed_z[0], a.far_thr2);
+                }
+                const unsigned keep = __ballot_sync(IKB_FULL_MASK, mine);
+                if (mine) {
+                    const int slot = (in_head + in_cnt + __popc(keep & lt)) & (IKB_Q - 1);
                     q.in_idx[slot] = (int)(cur + lane);
                     q.in_tr[slot] = (Real)planar_radius(x, y, ux, uy);
                     q.in_tz[slot] = (Real)z;
                 }
-                in_cnt += m;
+                in_cnt += __popc(keep);
                 cur += m;
                 __syncwarp();
             }
@@ -517,6 +546,156 @@ __global__ void __launch_bounds__(IKB_FABRIK_WARPS * 32, (CHAINS == 1 ? IKB_FABR
             atomicAdd(&a.stats->sum_fk_error, es);
             atomicAdd(&a.stats->n_fk_error, (unsigned long long)ec);
         }
+    }
+}
+
+template <typename Real, int CHAINS, bool FUSE_FK>
+__global__ void __launch_bounds__(IKB_FABRIK_WARPS * 32, (CHAINS == 1 ? IKB_FABRIK_MIN_CTAS : IKB_FABRIK_MIN_CTAS2))
+    fabrik_planar_kernel(const FabrikArgs a)
+{
+    __shared__ WarpQueues<Real, 32 + 32 * CHAINS> s_queues[IKB_FABRIK_WARPS];
+    fabrik_refill_loop<Real, CHAINS, FUSE_FK>(a, s_queues);
+}
+
+// ---- out-of-reach targets: max_iter passes in lockstep (see is_far) -----------------------------------------
+#ifndef IKB_FAR_CHAINS
+#define IKB_FAR_CHAINS 2
+#endif
+#ifndef IKB_FAR_MIN_CTAS
+#define IKB_FAR_MIN_CTAS 3
+#endif
+
+template <typename Real>
+struct FarQueue {
+    int idx[32 * IKB_FAR_CHAINS + 32];
+    Real tr[32 * IKB_FAR_CHAINS + 32], tz[32 * IKB_FAR_CHAINS + 32];
+    Real out_c[4][32 * IKB_FAR_CHAINS];
+};
+
+template <typename Real>
+__device__ __forceinline__ void fabrik_far_loop(const FabrikArgs &a, FarQueue<Real> *s_q)
+{
+    constexpr int CH = IKB_FAR_CHAINS, BATCH = 32 * CH;
+    FarQueue<Real> &q = s_q[threadIdx.x >> 5];
+    const int lane = threadIdx.x & 31;
+    const unsigned lt = ikb_lanemask_lt();
+    const IkbRobot &rc = a.rc;
+    const Real R0 = (Real)rc.seed_r[0], Z0 = (Real)rc.seed_z[0];
+    const Real d1 = (Real)rc.links[1], d2 = (Real)rc.links[2];
+    const Band<Real> start_band = make_band<Real>(rc, 0), goal_band = make_band<Real>(rc, 1);
+    const int max_iter = rc.max_iter;
+    long long cur = 0, cur_end = 0;
+    int cnt = 0;  // queued targets, always at the front of the arrays
+    bool exhausted = false;
+    unsigned solved_local = 0;
+    double fk_sum = 0.0;
+    unsigned fk_cnt = 0;
+    for (;;) {
+        // stage far targets until a full batch is queued (or the input is exhausted)
+        while (cnt < BATCH && !exhausted) {
+            if (cur == cur_end) {
+                unsigned long long base = 0;
+                if (lane == 0)
+                    base = atomicAdd(a.work_counter_far, (unsigned long long)IKB_FABRIK_CHUNK);
+                base = __shfl_sync(IKB_FULL_MASK, base, 0);
+                if ((long long)base >= a.n) {
+                    exhausted = true;
+                    break;
+                }
+                cur = (long long)base;
+                cur_end = min(cur + IKB_FABRIK_CHUNK, a.n);
+            }
+            const int m = (int)min((long long)32, cur_end - cur);
+            double x = 0, y = 0, z = 0, ux, uy;
+            bool mine = false;
+            if (lane < m) {
+                ikb_load_xyz(a.xyz, a.xyz_f64, cur + lane, x, y, z);
+                mine = is_far(x, y, z, rc.seed_r[0], rc.seed_z[0], a.far_thr2);
+            }
+            const unsigned keep = __ballot_sync(IKB_FULL_MASK, mine);
+            if (mine) {
+                const int slot = cnt + __popc(keep & lt);
+                q.idx[slot] = (int)(cur + lane);
+                q.tr[slot] = (Real)planar_radius(x, y, ux, uy);
+                q.tz[slot] = (Real)z;
+            }
+            cnt += __popc(keep);
+            cur += m;
+            __syncwarp();
+        }
+        if (cnt == 0)
+            break;
+        // one batch: chain slot u of lane l takes entry u * 32 + l; empty slots run on a harmless dummy target
+        const int nb = min(cnt, BATCH);
+        PlanarChain<Real> c[CH];
+        Real Tr[CH], Tz[CH];
+#pragma unroll
+        for (int u = 0; u < CH; ++u) {
+            const int e = u * 32 + lane;
+            Tr[u] = e < nb ? q.tr[e] : (Real)100;
+            Tz[u] = e < nb ? q.tz[e] : (Real)100;
+            c[u].r1 = (Real)rc.seed_r[1]; c[u].z1 = (Real)rc.seed_z[1];
+            c[u].r2 = (Real)rc.seed_r[2]; c[u].z2 = (Real)rc.seed_z[2];
+        }
+#pragma unroll 1
+        for (int it = 0; it < max_iter; ++it) {
+#pragma unroll
+            for (int u = 0; u < CH; ++u)
+                (void)fabrik_pass(c[u], Tr[u], Tz[u], R0, Z0, d1, d2, start_band, goal_band);
+        }
+        // park the chains, then ONE epilogue call site for every entry (results must not depend on the chain slot)
+#pragma unroll
+        for (int u = 0; u < CH; ++u) {
+            const int e = u * 32 + lane;
+            q.out_c[0][e] = c[u].r1; q.out_c[1][e] = c[u].z1; q.out_c[2][e] = c[u].r2; q.out_c[3][e] = c[u].z2;
+        }
+        __syncwarp();
+#pragma unroll 1
+        for (int e = lane; e < nb; e += 32) {
+            fabrik_epilogue<false>(a, q.idx[e], max_iter, (double)q.out_c[0][e], (double)q.out_c[1][e],
+                                   (double)q.out_c[2][e], (double)q.out_c[3][e], fk_sum, fk_cnt);
+            ++solved_local;
+        }
+        __syncwarp();
+        // move the rest (< 32 entries) to the front
+        const int rest = cnt - nb;
+        int m_idx = 0;
+        Real m_tr = 0, m_tz = 0;
+        if (lane < rest) { m_idx = q.idx[nb + lane]; m_tr = q.tr[nb + lane]; m_tz = q.tz[nb + lane]; }
+        __syncwarp();
+        if (lane < rest) { q.idx[lane] = m_idx; q.tr[lane] = m_tr; q.tz[lane] = m_tz; }
+        __syncwarp();
+        cnt = rest;
+    }
+    const unsigned sv = ikb_warp_sum(solved_local);
+    if (lane == 0 && sv != 0) {
+        atomicAdd(&a.stats->sum_iterations, (unsigned long long)sv * (unsigned long long)max_iter);
+        atomicAdd(&a.stats->n_solved, (unsigned long long)sv);
+        atomicAdd(&a.stats->n_iter_capped, (unsigned long long)sv);
+    }
+}
+
+// One launch for both populations: a CTA starts in one role and, when the rows of its role are used up, carries on
+// in the other, so the two populations balance themselves whatever the mix.  Each role scans the whole input through
+// its own chunk counter and claims its rows with is_far.  (Which role a CTA starts in hardly matters -- 17.1 to
+// 17.7 ms per 1e8 rows across 0..100 % -- because a lockstep warp is bound by the latency of its own dependent fp64
+// chain rather than by the pipe once fewer than six of them share a scheduler.)
+template <typename Real>
+__global__ void __launch_bounds__(IKB_FABRIK_WARPS * 32, IKB_FABRIK_MIN_CTAS) fabrik_split_kernel(const FabrikArgs a)
+{
+    constexpr size_t kNear = sizeof(WarpQueues<Real, 64>) * IKB_FABRIK_WARPS, kFar = sizeof(FarQueue<Real>) * IKB_FABRIK_WARPS;
+    __shared__ __align__(16) unsigned char s_raw[kNear > kFar ? kNear : kFar];
+#ifndef IKB_SPLIT_FAR_PCT
+#define IKB_SPLIT_FAR_PCT 34
+#endif
+    const bool far_first = blockIdx.x * 100u < gridDim.x * (unsigned)IKB_SPLIT_FAR_PCT;
+#pragma unroll 1
+    for (int phase = 0; phase < 2; ++phase) {
+        if ((phase == 0) == far_first)
+            fabrik_far_loop<Real>(a, reinterpret_cast<FarQueue<Real> *>(s_raw));
+        else
+            fabrik_refill_loop<Real, 1, false>(a, reinterpret_cast<WarpQueues<Real, 64> *>(s_raw));
+        __syncthreads();  // the two roles overlay the same shared memory
     }
 }
 
@@ -706,6 +885,12 @@ __global__ void __launch_bounds__(128) fabrik_generic_ikine_kernel(const FabrikG
 }  // namespace
 
 // ---- launchers (called from capi.cu) --------------------------------------------------------------
+// Rows below which the out-of-reach split is not worth a second launch.
+#ifndef IKB_SPLIT_MIN_ROWS
+#define IKB_SPLIT_MIN_ROWS 65536
+#endif
+
+// work_counter: TWO consecutive counters (lane-refill kernel, far kernel).
 cudaError_t ikb_launch_fabrik_planar(const void *xyz, int xyz_f64, long long n, long long index_base,
                                      void *angles, int angles_f64, int *iters, void *fk_err, int fk_stats,
                                      int precision, IkbDeviceStats *stats, unsigned long long *work_counter,
@@ -718,16 +903,31 @@ cudaError_t ikb_launch_fabrik_planar(const void *xyz, int xyz_f64, long long n, 
     a.angles = angles; a.angles_f64 = angles_f64; a.iters = iters;
     a.fk_err = fk_err; a.fk_stats = fk_stats;
     a.stats = stats; a.work_counter = work_counter; a.rc = rc;
-    cudaError_t err = cudaMemsetAsync(work_counter, 0, sizeof(unsigned long long), stream);
+    a.far_thr2 = -1.0;
+    a.work_counter_far = nullptr;
+    cudaError_t err = cudaMemsetAsync(work_counter, 0, 2 * sizeof(unsigned long long), stream);
     if (err != cudaSuccess)
         return err;
+    const bool fuse = fk_err != nullptr || fk_stats != 0;  // the caller checked rc.fk_planar_tail
+    static const bool split_enabled = [] { const char *v = std::getenv("IKB_FABRIK_SPLIT"); return !v || v[0] != '0'; }();
+    const bool split = split_enabled && !fuse && n >= IKB_SPLIT_MIN_ROWS && !rc.zero_iter && rc.max_iter >= 8;
     // persistent grid: resident CTAs per SM x SM count, trimmed for small batches
     const int per_cta = IKB_FABRIK_WARPS * 32;
     long long want = (n + per_cta - 1) / per_cta;
     long long grid = (long long)num_sms * (IKB_FABRIK_CHAINS == 1 ? IKB_FABRIK_MIN_CTAS : IKB_FABRIK_MIN_CTAS2);
     if (want < grid)
         grid = want;
-    const bool fuse = fk_err != nullptr || fk_stats != 0;  // the caller checked rc.fk_planar_tail
+    if (split) {
+        const double reach = rc.links[1] + rc.links[2] + rc.links[3];
+        const double thr = reach + rc.tol + 1e-6 * (1.0 + reach);  // margin >> the rounding of |f2 - S| <= d1 + d2
+        a.far_thr2 = thr * thr;
+        a.work_counter_far = work_counter + 1;
+        if (precision == IKB_FABRIK_F32)
+            fabrik_split_kernel<float><<<(unsigned)grid, per_cta, 0, stream>>>(a);
+        else
+            fabrik_split_kernel<double><<<(unsigned)grid, per_cta, 0, stream>>>(a);
+        return cudaGetLastError();
+    }
     if (precision == IKB_FABRIK_F32) {
         if (fuse)
             fabrik_planar_kernel<float, IKB_FABRIK_CHAINS, true><<<(unsigned)grid, per_cta, 0, stream>>>(a);

@@ -80,7 +80,7 @@ def _robot():
     return R
 
 
-@pytest.mark.parametrize("n", [5_001, 100_000])  # below / above the row count where K1 fuses the error (capi.cu)
+@pytest.mark.parametrize("n", [501, 100_000])  # below / above the row count where K1 fuses the error (capi.cu)
 @pytest.mark.parametrize("dtype", [np.float32, np.float64])
 def test_fabrik_fused_fk_error_equals_k3(dtype, n):
     from inversekinematicsann_b200.kinematics.forward import ForwardKinematics
@@ -141,7 +141,7 @@ def test_device_entry_points_fk_stats_only():
     from inversekinematicsann_b200.kinematics._shared import get_engine
     eng = get_engine()
     g = torch.Generator(device="cuda").manual_seed(4)
-    xyz = torch.rand(10_000, 3, device="cuda", generator=g) * torch.tensor([6.0, 12.0, 9.0], device="cuda") + \
+    xyz = torch.rand(1_000, 3, device="cuda", generator=g) * torch.tensor([6.0, 12.0, 9.0], device="cuda") + \
         torch.tensor([0.0, -6.0, -3.0], device="cuda")
     ang = torch.empty(xyz.shape[0], 4, device="cuda")
     err = torch.empty(xyz.shape[0], device="cuda")
