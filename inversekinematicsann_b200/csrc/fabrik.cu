@@ -89,23 +89,25 @@ __device__ __forceinline__ bool fabrik_pass(PlanarChain<Real> &c, Real Tr, Real 
                                             const Band<Real> &goal_band)
 {
     // backward (fabrik.py:19-29): b3 = T, b2 = PB(b3, P2, d2), b1 = PB(b2, P1, d1), b0 = PB(b1, P0, d0)
+    // (this file is compiled with --fmad=false: every fused multiply-add is written out, so that a row's result does
+    //  not depend on which kernel, or which inlined copy of this function, happens to process it)
     Real dr = c.r2 - Tr, dz = c.z2 - Tz;
-    Real s = d2 * ikb_rsqrt(dr * dr + dz * dz);
-    const Real b2r = Tr + s * dr, b2z = Tz + s * dz;
+    Real s = d2 * ikb_rsqrt(fma(dz, dz, dr * dr));
+    const Real b2r = fma(s, dr, Tr), b2z = fma(s, dz, Tz);
     dr = c.r1 - b2r; dz = c.z1 - b2z;
-    s = d1 * ikb_rsqrt(dr * dr + dz * dz);
-    const Real b1r = b2r + s * dr, b1z = b2z + s * dz;
+    s = d1 * ikb_rsqrt(fma(dz, dz, dr * dr));
+    const Real b1r = fma(s, dr, b2r), b1z = fma(s, dz, b2z);
     dr = R0 - b1r; dz = Z0 - b1z;
-    Real n2 = dr * dr + dz * dz;
+    Real n2 = fma(dz, dz, dr * dr);
     const bool start_off = start_band.outside(n2);                       // fabrik.py:61
     // forward (fabrik.py:32-42): f0 = S, f1 = PB(f0, b1, d1), f2 = PB(f1, b2, d2), f3 = PB(f2, b3, d3)
     s = d1 * ikb_rsqrt(n2);
-    c.r1 = R0 - s * dr; c.z1 = Z0 - s * dz;  // (b1 - S) = -(dr, dz)
+    c.r1 = fma(-s, dr, R0); c.z1 = fma(-s, dz, Z0);  // (b1 - S) = -(dr, dz)
     dr = b2r - c.r1; dz = b2z - c.z1;
-    s = d2 * ikb_rsqrt(dr * dr + dz * dz);
-    c.r2 = c.r1 + s * dr; c.z2 = c.z1 + s * dz;
+    s = d2 * ikb_rsqrt(fma(dz, dz, dr * dr));
+    c.r2 = fma(s, dr, c.r1); c.z2 = fma(s, dz, c.z1);
     dr = Tr - c.r2; dz = Tz - c.z2;
-    n2 = dr * dr + dz * dz;                   // f3 itself is only needed after the last pass
+    n2 = fma(dz, dz, dr * dr);                // f3 itself is only needed after the last pass
     return start_off | goal_band.outside(n2);                            // fabrik.py:63
 }
 
@@ -136,7 +138,7 @@ __device__ __forceinline__ double fast_div(double a, double b)
 __device__ __forceinline__ double dist2d(double ar, double az, double br, double bz)
 {
     const double dr = ar - br, dz = az - bz;
-    return fast_sqrt(dr * dr + dz * dz);
+    return fast_sqrt(fma(dz, dz, dr * dr));
 }
 
 // round(x, 8) of reference inverse.py:81,92,100: q = rint(x * 1e8) is an integer, q / 1e8 is formed as
@@ -200,7 +202,7 @@ __device__ __forceinline__ double atan2_unit(double uy, double ux)
 // have no direction (the reference's theta_1 is rounding noise there): +x is used.
 __device__ __forceinline__ double planar_radius(double x, double y, double &ux, double &uy)
 {
-    const double n2 = x * x + y * y;
+    const double n2 = fma(y, y, x * x);
     const double rs = ikb_rsqrt(n2);
     const bool on_axis = (n2 == 0.0);
     ux = on_axis ? 1.0 : x * rs;
@@ -268,10 +270,10 @@ __device__ __forceinline__ void fabrik_epilogue(const FabrikArgs &a, int idx, in
         r3 = rc.seed_r[3]; z3 = rc.seed_z[3];
     } else {       // f3 = PB(f2, T, d3) (fabrik.py:40)
         const double dr = Tr - r2, dz = Tz - z2;
-        const double n2 = dr * dr + dz * dz;
+        const double n2 = fma(dz, dz, dr * dr);
         zero_div |= (n2 == 0.0);
         const double s = rc.links[3] * ikb_rsqrt(n2);
-        r3 = r2 + s * dr; z3 = z2 + s * dz;
+        r3 = fma(s, dr, r2); z3 = fma(s, dz, z2);
     }
     // a NaN chain from finite input can only come from 0 * inf, i.e. a zero-length segment
     const bool finite_in = isfinite(x) & isfinite(y) & isfinite(z);
@@ -283,23 +285,23 @@ __device__ __forceinline__ void fabrik_epilogue(const FabrikArgs &a, int idx, in
     const double ab = rc.seed_ab;                                        // |AB|, A = origin: a constant
     const double bc = dist2d(R0, Z0, r1, z1), cd = dist2d(r1, z1, r2, z2);
     const double de = dist2d(r2, z2, r3, z3);
-    const double ac = fast_sqrt(r1 * r1 + z1 * z1);
+    const double ac = fast_sqrt(fma(z1, z1, r1 * r1));
     const double bd = dist2d(R0, Z0, r2, z2), ce = dist2d(r1, z1, r3, z3);
     double den = 2 * ab * bc;
     zero_div |= (den == 0.0);
-    const double c2 = round8(fast_div(ab * ab + bc * bc - ac * ac, den));   // inverse.py:77-81
+    const double c2 = round8(fast_div(fma(-ac, ac, fma(bc, bc, ab * ab)), den));   // inverse.py:77-81
     const double acos2 = acos_fast(c2);
     th[1] = ((r1 * ux) * (r2 * ux) < 0) ? (3 * PI / 2) - acos2 : -(PI / 2 - acos2);  // :82-85
     den = 2 * bc * cd;
     zero_div |= (den == 0.0);
-    const double c3 = round8(fast_div(bc * bc + cd * cd - bd * bd, den));   // :90-92
+    const double c3 = round8(fast_div(fma(-bd, bd, fma(cd, cd, bc * bc)), den));   // :90-92
     th[2] = -(PI - acos_fast(c3));                                            // :93
     den = 2 * cd * de;
     zero_div |= (den == 0.0) | (ce == 0.0);
-    const double c4 = round8(fast_div(cd * cd + de * de - ce * ce, den));   // :98-100
+    const double c4 = round8(fast_div(fma(-ce, ce, fma(de, de, cd * cd)), den));   // :98-100
     const double acos4 = acos_fast(c4);
     // t4_point_bt = PB(C, E, |CE| / 2) (inverse.py:102): (|CE|/2)/|CE| is exactly 0.5
-    const double mr = r1 + 0.5 * (r3 - r1), mz = z1 + 0.5 * (z3 - z1);
+    const double mr = fma(0.5, r3 - r1, r1), mz = fma(0.5, z3 - z1, z1);
     const double dista = dist2d(R0, Z0, mr, mz);
     th[3] = (bd > dista) ? -(PI - acos4) : (PI - acos4);                 // :103-108
     zero_div &= finite_in;

@@ -313,3 +313,35 @@ def test_non_planar_robot_takes_the_generic_kernel():
     assert ikg.last_stats.n_solved == len(xyz) and ikg.last_stats.sum_iterations == int(iters.sum())
     with pytest.raises(OutOfRobotReachException):
         ikg.ikine([[1, 2, 3], [1, 2, 7]])
+
+
+def test_out_of_reach_split_is_value_identical(ik):
+    """Batches >= 65 536 rows run the split kernel (out-of-reach targets in lockstep, csrc/fabrik.cu is_far), smaller
+    ones the lane-refill kernel alone: the same rows must come out identical, in particular in the thin shell
+    around |T - S| = d1 + d2 + d3 + tol where the predicate flips."""
+    rng = np.random.RandomState(77)
+    n = 90_000
+    xyz = rng.rand(n, 3) * [6, 12, 9] + [0, -6, -3]
+    # shell: distance from S = (0, 0, 2) within +-2e-3 of the reach limit 6 + tol, directions inside the workspace
+    m = 30_000
+    d = rng.randn(m, 3)
+    d[:, 0] = np.abs(d[:, 0])
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    radius = 6.001 + rng.uniform(-2e-3, 2e-3, m)
+    radius[:2000] = 6.001 + rng.uniform(-1e-5, 1e-5, 2000)
+    shell = np.array([0.0, 0.0, 2.0]) + d * radius[:, None]
+    ok = (shell[:, 0] <= 6) & (np.abs(shell[:, 1]) <= 6) & (shell[:, 2] >= -3) & (shell[:, 2] <= 6)
+    xyz[:int(ok.sum())] = shell[ok]
+    rng.shuffle(xyz)
+    whole, it_whole = ik.ikine(xyz, as_array=True, return_iterations=True)
+    parts = [ik.ikine(xyz[i:i + 30_000], as_array=True, return_iterations=True) for i in range(0, n, 30_000)]
+    pieces = np.concatenate([p[0] for p in parts])
+    it_pieces = np.concatenate([p[1] for p in parts])
+    assert np.array_equal(it_whole, it_pieces)
+    assert np.array_equal(whole, pieces, equal_nan=True)
+    far = np.linalg.norm(xyz - [0, 0, 2], axis=1) > 6.0011
+    assert (it_whole[far] == 100).all() and far.sum() > 20_000
+    from oracle import c_oracle
+    want = c_oracle.fabrik_ikine(xyz)
+    assert np.array_equal(it_whole, want["iters"])
+    assert np.abs(whole - want["angles"]).max() <= TOL_F64_MODE
