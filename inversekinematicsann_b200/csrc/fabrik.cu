@@ -318,15 +318,14 @@ __device__ __forceinline__ void fabrik_epilogue(const FabrikArgs &a, int idx, in
     if (FUSE_FK) {  // fused K3: FK of the angles as stored, in the stored precision
         double err;
         if (a.angles_f64) {
-            err = fused_fk_error_f64(th[0], th[1], th[2], th[3], x, y, z, rc.a[0], rc.a[1], rc.a[2], rc.a[3], rc.eps[0],
-                                     rc.eps[1] + rc.eps[2] + rc.eps[3], rc.cos_alpha[0], rc.sin_alpha[0]);
+            err = fused_fk_error_f64(th[0], th[1], th[2], th[3], x, y, z, rc.fkc[0], rc.fkc[1], rc.fkc[2], rc.fkc[3],
+                                     rc.fkc[4], rc.fkc[5], rc.fkc[6], rc.fkc[7]);
             if (a.fk_err)
                 reinterpret_cast<double *>(a.fk_err)[idx] = err;
         } else {
             const float e = fused_fk_error_f32((float)th[0], (float)th[1], (float)th[2], (float)th[3], (float)x, (float)y,
-                                               (float)z, (float)rc.a[0], (float)rc.a[1], (float)rc.a[2], (float)rc.a[3],
-                                               (float)rc.eps[0], (float)(rc.eps[1] + rc.eps[2] + rc.eps[3]),
-                                               (float)rc.cos_alpha[0], (float)rc.sin_alpha[0]);
+                                               (float)z, rc.fkc_f[0], rc.fkc_f[1], rc.fkc_f[2], rc.fkc_f[3], rc.fkc_f[4],
+                                               rc.fkc_f[5], rc.fkc_f[6], rc.fkc_f[7]);
             if (a.fk_err)
                 reinterpret_cast<float *>(a.fk_err)[idx] = e;
             err = (double)e;

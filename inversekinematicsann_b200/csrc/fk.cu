@@ -34,9 +34,12 @@ struct FkArgs {
 #define FK_MINB 4
 #endif
 
-template <typename Real>
+// Real = dtype of the angle / position / error buffers, XYZ_F64 = dtype of the target buffer: both compile-time, so the
+// row loop carries no dtype branches.
+template <typename Real, bool XYZ_F64>
 __global__ void __launch_bounds__(256, FK_MINB) fk_kernel(const FkArgs a)
 {
+    constexpr bool ANG_F64 = sizeof(Real) == 8;
     const long long stride = (long long)gridDim.x * blockDim.x;
     double err_sum = 0.0;
     unsigned err_cnt = 0;
@@ -52,7 +55,7 @@ __global__ void __launch_bounds__(256, FK_MINB) fk_kernel(const FkArgs a)
         for (int u = 0; u < FK_ROWS; ++u) {
             const long long i = base + u * stride;
             if (i < a.n) {
-                if (a.angles_f64) {
+                if (ANG_F64) {
                     const double2 *p = reinterpret_cast<const double2 *>(a.angles) + 2 * i;
                     const double2 v0 = __ldg(p), v1 = __ldg(p + 1);
                     th[u][0] = (Real)v0.x; th[u][1] = (Real)v0.y; th[u][2] = (Real)v1.x; th[u][3] = (Real)v1.y;
@@ -61,7 +64,7 @@ __global__ void __launch_bounds__(256, FK_MINB) fk_kernel(const FkArgs a)
                     th[u][0] = (Real)v.x; th[u][1] = (Real)v.y; th[u][2] = (Real)v.z; th[u][3] = (Real)v.w;
                 }
                 if (a.targets) {
-                    if (a.xyz_f64) {
+                    if (XYZ_F64) {
                         const double *p = reinterpret_cast<const double *>(a.targets) + 3 * i;
                         tg[u][0] = (Real)__ldg(p); tg[u][1] = (Real)__ldg(p + 1); tg[u][2] = (Real)__ldg(p + 2);
                     } else {  // no detour through double for fp32 buffers
@@ -83,7 +86,7 @@ __global__ void __launch_bounds__(256, FK_MINB) fk_kernel(const FkArgs a)
                 atomicMin(&a.stats->first_fk_angle_range, a.index_base + i);
             }
             if (a.pos_out) {
-                if (a.angles_f64) {
+                if (ANG_F64) {
                     double *o = reinterpret_cast<double *>(a.pos_out) + 3 * i;
                     o[0] = px; o[1] = py; o[2] = pz;
                 } else {
@@ -95,7 +98,7 @@ __global__ void __launch_bounds__(256, FK_MINB) fk_kernel(const FkArgs a)
                 const Real dx = px - tg[u][0], dy = py - tg[u][1], dz = pz - tg[u][2];
                 const Real err = sqrt(dx * dx + dy * dy + dz * dz);
                 if (a.err_out) {
-                    if (a.angles_f64)
+                    if (ANG_F64)
                         reinterpret_cast<double *>(a.err_out)[i] = err;
                     else
                         reinterpret_cast<float *>(a.err_out)[i] = (float)err;
@@ -229,10 +232,17 @@ cudaError_t ikb_launch_fk(const void *angles, int angles_f64, long long n, long 
     a.pos_out = pos_out; a.targets = targets; a.xyz_f64 = xyz_f64; a.err_out = err_out;
     a.stats = stats; a.rc = rc;
     const unsigned grid = ikb_stream_grid(n, num_sms, 256, 8);
-    if (angles_f64)
-        fk_kernel<double><<<grid, 256, 0, stream>>>(a);
-    else
-        fk_kernel<float><<<grid, 256, 0, stream>>>(a);
+    if (angles_f64) {
+        if (xyz_f64)
+            fk_kernel<double, true><<<grid, 256, 0, stream>>>(a);
+        else
+            fk_kernel<double, false><<<grid, 256, 0, stream>>>(a);
+    } else {
+        if (xyz_f64)
+            fk_kernel<float, true><<<grid, 256, 0, stream>>>(a);
+        else
+            fk_kernel<float, false><<<grid, 256, 0, stream>>>(a);
+    }
     return cudaGetLastError();
 }
 

@@ -10,10 +10,13 @@
 // integer instructions made the fp32 FK kernel instruction-bound instead of HBM-bound.
 __device__ __forceinline__ void ikb_sincos(float x, float *s, float *c)
 {
-    const float k = rintf(x * 0.63661977236758134f);
+    // k = rint(x 2/pi) through the 1.5 * 2^23 trick: the sum's low mantissa bits ARE k (two's complement), so neither
+    // a round nor a float-to-int conversion (both quarter-rate XU instructions) is needed; |x| <= 2 pi keeps |k| <= 4
+    const float t = fmaf(x, 0.63661977236758134f, 12582912.0f);
+    const int q = __float_as_int(t);
+    const float k = t - 12582912.0f;
     float r = fmaf(k, -1.57079625129699707031f, x);
     r = fmaf(k, -7.54978941586159635335e-8f, r);
-    const int q = (int)k;
     const float r2 = r * r;
     float sp = fmaf(r2, -1.9515295891e-4f, 8.3321608736e-3f);
     sp = fmaf(sp, r2, -1.6666654611e-1f);
@@ -67,7 +70,7 @@ __device__ __forceinline__ Real ikb_fk_error_planar_tail(const Real th[4], Real 
     Real s[4], c[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-        ok &= !(th[i] < -TWO_PI) & !(th[i] > TWO_PI);
+        ok &= !(fabs(th[i]) > TWO_PI);
         ikb_sincos(th[i], &s[i], &c[i]);
     }
     Real px, py, pz;
@@ -76,6 +79,13 @@ __device__ __forceinline__ Real ikb_fk_error_planar_tail(const Real th[4], Real 
     const Real err = sqrt(dx * dx + dy * dy + dz * dz);
     return ok ? err : (Real)__int_as_float(0x7fc00000);
 }
+
+template <typename Real>
+__device__ __forceinline__ const Real *fk_constants(const IkbRobot &rc);
+template <>
+__device__ __forceinline__ const double *fk_constants<double>(const IkbRobot &rc) { return rc.fkc; }
+template <>
+__device__ __forceinline__ const float *fk_constants<float>(const IkbRobot &rc) { return rc.fkc_f; }
 
 // Position-only DH chain.  General form: p += R [a c, a s, eps]; R = R Rz(theta) Rx(alpha).
 // When joints 2..4 have alpha == 0 (rc.fk_planar_tail: every arm of the reference's family, robot.py:40) the
@@ -93,13 +103,12 @@ __device__ __forceinline__ bool fk_position(const IkbRobot &rc, const Real th[4]
     Real s[4], c[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-        ok &= !(th[i] < -TWO_PI) & !(th[i] > TWO_PI);  // forward.py:23-25 (NaN passes, as upstream)
+        ok &= !(fabs(th[i]) > TWO_PI);  // forward.py:23-25 (NaN passes, as upstream)
         ikb_sincos(th[i], &s[i], &c[i]);
     }
     if (rc.fk_planar_tail) {
-        fk_planar_tail_position<Real>(s, c, (Real)rc.a[0], (Real)rc.a[1], (Real)rc.a[2], (Real)rc.a[3], (Real)rc.eps[0],
-                                      (Real)(rc.eps[1] + rc.eps[2] + rc.eps[3]), (Real)rc.cos_alpha[0],
-                                      (Real)rc.sin_alpha[0], px, py, pz);
+        const Real *k = fk_constants<Real>(rc);
+        fk_planar_tail_position<Real>(s, c, k[0], k[1], k[2], k[3], k[4], k[5], k[6], k[7], px, py, pz);
         return ok;
     }
     Real R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};

@@ -31,6 +31,10 @@ struct IkbRobot {
     // forward kinematics, reference forward.py:62-70: T_i = Rz(th_i) Tz(eps_i) Tx(a_i) Rx(alpha_i)
     double eps[4], a[4], cos_alpha[4], sin_alpha[4], alpha[4];
     int fk_planar_tail;   // alpha[1..3] == 0: joints 2..4 rotate about parallel axes (closed-form FK)
+    // the closed form's constants: a[0..3], eps[0], eps[1]+eps[2]+eps[3], cos/sin alpha[0] -- in both precisions, so
+    // that the fp32 kernels read them from the constant bank instead of converting doubles per row
+    double fkc[8];
+    float fkc_f[8];
 };
 
 // Device-side statistics block; host mirror is ikb_stats.  first_* start at IKB_I64_MAX.
