@@ -280,7 +280,10 @@ __device__ __forceinline__ void fabrik_epilogue(const FabrikArgs &a, int idx, in
     zero_div |= finite_in & !(isfinite(r1) & isfinite(z1) & isfinite(r2) & isfinite(z2));
     double th[4];
     // theta_1 = atan2(E.y, E.x) with E = r3 (ux, uy) (inverse.py:60): only the sign of r3 matters
-    th[0] = r3 < 0.0 ? atan2_unit(-uy, -ux) : atan2_unit(uy, ux);
+    {
+        const bool flip = r3 < 0.0;  // one evaluation: the compiler will not merge two calls under a select
+        th[0] = atan2_unit(flip ? -uy : uy, flip ? -ux : ux);
+    }
     th[0] = r3 == 0.0 ? 0.0 : (r3 != r3 ? r3 : th[0]);
     const double ab = rc.seed_ab;                                        // |AB|, A = origin: a constant
     const double bc = dist2d(R0, Z0, r1, z1), cd = dist2d(r1, z1, r2, z2);
