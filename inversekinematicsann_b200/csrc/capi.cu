@@ -38,6 +38,21 @@ namespace {
 
 constexpr int kCounterRing = 16;
 constexpr long long kHostChunkRows = 1LL << 22;  // rows per pipeline stage of the *_host entry points
+
+// Rows of the pipeline stage that starts at row `lo`: full-size stages, except that a long call ramps up through two
+// short ones so that the device-to-host stream (the PCIe-bound direction: 16 B of angles per row) starts after a
+// tenth of a stage time instead of a whole one.
+inline long long host_chunk_rows(long long lo, long long n)
+{
+    long long m = kHostChunkRows;
+    if (n > 4 * kHostChunkRows) {
+        if (lo == 0)
+            m = kHostChunkRows / 8;
+        else if (lo == kHostChunkRows / 8)
+            m = kHostChunkRows / 2;
+    }
+    return std::min<long long>(m, n - lo);
+}
 constexpr int kSlots = 3;
 
 std::string g_create_error;
@@ -362,9 +377,9 @@ int ikb_check_limits_host(ikb_engine *e, const void *xyz, int xyz_dtype, int64_t
         return rc;
     const size_t row = 3 * esize(xyz_dtype);
     int it = 0;
-    for (long long lo = 0; lo < n; lo += kHostChunkRows, ++it) {
+    for (long long lo = 0, m = 0; lo < n; lo += m, ++it) {
         Slot &s = e->slots[it % kSlots];
-        const long long m = std::min<long long>(kHostChunkRows, n - lo);
+        m = host_chunk_rows(lo, n);
         IKB_CUDA(e, cudaMemcpyAsync(s.d_in, (const char *)xyz + lo * row, m * row, cudaMemcpyHostToDevice, s.stream));
         IKB_CUDA(e, ikb_launch_check_limits(s.d_in, xyz_dtype == IKB_F64, m, lo, e->d_stats, e->rc,
                                             e->num_sms, s.stream));
@@ -433,9 +448,9 @@ int ikb_fabrik_solve_host(ikb_engine *e, const void *xyz, int xyz_dtype, int64_t
     const bool want_fk = fk_err_out || fk_stats;
     const bool fuse = want_fk && e->rc.planar && fk_fusable(e->rc, n);
     int it = 0;
-    for (long long lo = 0; lo < n; lo += kHostChunkRows, ++it) {
+    for (long long lo = 0, m = 0; lo < n; lo += m, ++it) {
         Slot &s = e->slots[it % kSlots];
-        const long long m = std::min<long long>(kHostChunkRows, n - lo);
+        m = host_chunk_rows(lo, n);
         void *d_err = fk_err_out ? s.d_in2 : nullptr;  // d_in2 is free here (FK targets only)
         IKB_CUDA(e, cudaMemcpyAsync(s.d_in, (const char *)xyz + lo * in_row, m * in_row, cudaMemcpyHostToDevice, s.stream));
         if (!e->rc.planar)
@@ -517,9 +532,9 @@ int ikb_fk_host(ikb_engine *e, const void *angles, int angles_dtype, int64_t n, 
     const size_t a_row = 4 * esize(angles_dtype), p_row = 3 * esize(angles_dtype), t_row = 3 * esize(xyz_dtype);
     const size_t e_row = esize(angles_dtype);
     int it = 0;
-    for (long long lo = 0; lo < n; lo += kHostChunkRows, ++it) {
+    for (long long lo = 0, m = 0; lo < n; lo += m, ++it) {
         Slot &s = e->slots[it % kSlots];
-        const long long m = std::min<long long>(kHostChunkRows, n - lo);
+        m = host_chunk_rows(lo, n);
         IKB_CUDA(e, cudaMemcpyAsync(s.d_in, (const char *)angles + lo * a_row, m * a_row, cudaMemcpyHostToDevice, s.stream));
         if (targets)
             IKB_CUDA(e, cudaMemcpyAsync(s.d_in2, (const char *)targets + lo * t_row, m * t_row, cudaMemcpyHostToDevice, s.stream));
@@ -599,9 +614,9 @@ int ikb_ann_solve_host(ikb_engine *e, const void *xyz, int xyz_dtype, int64_t n,
         return rc;
     const size_t in_row = 3 * esize(xyz_dtype), out_row = 4 * sizeof(float);
     int it = 0;
-    for (long long lo = 0; lo < n; lo += kHostChunkRows, ++it) {
+    for (long long lo = 0, m = 0; lo < n; lo += m, ++it) {
         Slot &s = e->slots[it % kSlots];
-        const long long m = std::min<long long>(kHostChunkRows, n - lo);
+        m = host_chunk_rows(lo, n);
         float *d_err = fk_err_out ? (float *)s.d_in2 : nullptr;
         IKB_CUDA(e, cudaMemcpyAsync(s.d_in, (const char *)xyz + lo * in_row, m * in_row, cudaMemcpyHostToDevice, s.stream));
         std::string msg;
