@@ -255,6 +255,8 @@ int ikb_engine_create(const ikb_config *cfg, ikb_engine **out)
         rc.sin_alpha[j] = std::sin(rc.alpha[j]);
     }
     rc.fk_planar_tail = (rc.alpha[1] == 0.0 && rc.alpha[2] == 0.0 && rc.alpha[3] == 0.0) ? 1 : 0;
+    for (int j = 0; j < 4; ++j)
+        rc.link_k[j] = ikb_scaled_rsqrt_constants(cfg->links[j]);
     {
         const double fkc[8] = {rc.a[0], rc.a[1], rc.a[2], rc.a[3], rc.eps[0], rc.eps[1] + rc.eps[2] + rc.eps[3],
                                rc.cos_alpha[0], rc.sin_alpha[0]};

@@ -83,28 +83,44 @@ __device__ __forceinline__ Band<float> make_band<float>(const IkbRobot &rc, int 
 // Returns true when the reference's loop condition (start_error > tol or goal_error > tol) holds.
 // start_error = |b0 - S| = | |S - b1| - d0 | and goal_error = |f3 - T| = | |T - f2| - d3 |, because b0 and
 // f3 are the points at distance d0 / d3 from b1 / f2 towards S / T.
+// d / sqrt(n2): fp64 folds the link length into the correction step (ikb_rsqrt_times), fp32 is seed times d
+template <typename Real>
+struct LinkScale;
+template <>
+struct LinkScale<double> {
+    const IkbScaledRsqrt &k;  // in the kernel's parameter block: the DFMAs take the constants as c[][] operands
+    __device__ __forceinline__ explicit LinkScale(const IkbScaledRsqrt &kk) : k(kk) {}
+    __device__ __forceinline__ double over_sqrt(double n2) const { return ikb_rsqrt_times(n2, k); }
+};
+template <>
+struct LinkScale<float> {
+    float d;
+    __device__ __forceinline__ explicit LinkScale(const IkbScaledRsqrt &kk) : d((float)kk.d) {}
+    __device__ __forceinline__ float over_sqrt(float n2) const { return d * ikb_rsqrt(n2); }
+};
+
 template <typename Real>
 __device__ __forceinline__ bool fabrik_pass(PlanarChain<Real> &c, Real Tr, Real Tz, Real R0, Real Z0,
-                                            Real d1, Real d2, const Band<Real> &start_band,
-                                            const Band<Real> &goal_band)
+                                            const LinkScale<Real> &d1, const LinkScale<Real> &d2,
+                                            const Band<Real> &start_band, const Band<Real> &goal_band)
 {
     // backward (fabrik.py:19-29): b3 = T, b2 = PB(b3, P2, d2), b1 = PB(b2, P1, d1), b0 = PB(b1, P0, d0)
     // (this file is compiled with --fmad=false: every fused multiply-add is written out, so that a row's result does
     //  not depend on which kernel, or which inlined copy of this function, happens to process it)
     Real dr = c.r2 - Tr, dz = c.z2 - Tz;
-    Real s = d2 * ikb_rsqrt(fma(dz, dz, dr * dr));
+    Real s = d2.over_sqrt(fma(dz, dz, dr * dr));
     const Real b2r = fma(s, dr, Tr), b2z = fma(s, dz, Tz);
     dr = c.r1 - b2r; dz = c.z1 - b2z;
-    s = d1 * ikb_rsqrt(fma(dz, dz, dr * dr));
+    s = d1.over_sqrt(fma(dz, dz, dr * dr));
     const Real b1r = fma(s, dr, b2r), b1z = fma(s, dz, b2z);
     dr = R0 - b1r; dz = Z0 - b1z;
     Real n2 = fma(dz, dz, dr * dr);
     const bool start_off = start_band.outside(n2);                       // fabrik.py:61
     // forward (fabrik.py:32-42): f0 = S, f1 = PB(f0, b1, d1), f2 = PB(f1, b2, d2), f3 = PB(f2, b3, d3)
-    s = d1 * ikb_rsqrt(n2);
+    s = d1.over_sqrt(n2);
     c.r1 = fma(-s, dr, R0); c.z1 = fma(-s, dz, Z0);  // (b1 - S) = -(dr, dz)
     dr = b2r - c.r1; dz = b2z - c.z1;
-    s = d2 * ikb_rsqrt(fma(dz, dz, dr * dr));
+    s = d2.over_sqrt(fma(dz, dz, dr * dr));
     c.r2 = fma(s, dr, c.r1); c.z2 = fma(s, dz, c.z1);
     dr = Tr - c.r2; dz = Tz - c.z2;
     n2 = fma(dz, dz, dr * dr);                // f3 itself is only needed after the last pass
@@ -272,7 +288,7 @@ __device__ __forceinline__ void fabrik_epilogue(const FabrikArgs &a, int idx, in
         const double dr = Tr - r2, dz = Tz - z2;
         const double n2 = fma(dz, dz, dr * dr);
         zero_div |= (n2 == 0.0);
-        const double s = rc.links[3] * ikb_rsqrt(n2);
+        const double s = ikb_rsqrt_times(n2, rc.link_k[3]);
         r3 = fma(s, dr, r2); z3 = fma(s, dz, z2);
     }
     // a NaN chain from finite input can only come from 0 * inf, i.e. a zero-length segment
@@ -373,7 +389,7 @@ __device__ __forceinline__ void fabrik_refill_loop(const FabrikArgs &a, WarpQueu
     }
     const IkbRobot &rc = a.rc;
     const Real R0 = (Real)rc.seed_r[0], Z0 = (Real)rc.seed_z[0];
-    const Real d1 = (Real)rc.links[1], d2 = (Real)rc.links[2];
+    const LinkScale<Real> d1(rc.link_k[1]), d2(rc.link_k[2]);
     const Band<Real> start_band = make_band<Real>(rc, 0), goal_band = make_band<Real>(rc, 1);
     const int max_iter = rc.max_iter;
     const bool zero_iter = rc.zero_iter != 0;
@@ -585,7 +601,7 @@ __device__ __forceinline__ void fabrik_far_loop(const FabrikArgs &a, FarQueue<Re
     const unsigned lt = ikb_lanemask_lt();
     const IkbRobot &rc = a.rc;
     const Real R0 = (Real)rc.seed_r[0], Z0 = (Real)rc.seed_z[0];
-    const Real d1 = (Real)rc.links[1], d2 = (Real)rc.links[2];
+    const LinkScale<Real> d1(rc.link_k[1]), d2(rc.link_k[2]);
     const Band<Real> start_band = make_band<Real>(rc, 0), goal_band = make_band<Real>(rc, 1);
     const int max_iter = rc.max_iter;
     long long cur = 0, cur_end = 0;

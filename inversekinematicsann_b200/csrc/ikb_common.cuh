@@ -10,6 +10,12 @@
 
 // Robot / solver constants handed to every kernel by value (kernel parameter space, broadcast
 // through the constant bank).  Derived once on the host from ikb_config.
+// d / sqrt(x) constants of ikb_rsqrt_times (below): d, d/2, 3d/8 -- precomputed on the host for every link length so
+// that the kernels use them straight from the parameter block
+struct IkbScaledRsqrt {
+    double d, d_half, d_38;
+};
+
 struct IkbRobot {
     // seed chain of FabrikInverseKinematics.ikine (reference inverse.py:123-130): FK of
     // [theta_1, dh[0][1], dh[0][2], dh[0][3]].  Rz(theta_1) is the left-most factor of the DH
@@ -35,6 +41,7 @@ struct IkbRobot {
     // that the fp32 kernels read them from the constant bank instead of converting doubles per row
     double fkc[8];
     float fkc_f[8];
+    IkbScaledRsqrt link_k[4];  // per link length: see ikb_rsqrt_times
 };
 
 // Device-side statistics block; host mirror is ikb_stats.  first_* start at IKB_I64_MAX.
@@ -112,6 +119,21 @@ __device__ __forceinline__ float ikb_rsqrt(float x)
     float y;
     asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
+}
+
+// d / sqrt(x) with the same seed and the same third-order correction, the factor folded into the correction's
+// constants:  d y (1 + e/2 + 3 e^2 / 8) = y (d + e (d/2 + (3d/8) e)) -- 5 DP instructions for the scaled result
+// instead of 6 (rsqrt, then times d).  The pass loop of K1 is bound by the fp64 pipe, so this is 1 of 12 per update.
+__host__ __device__ inline IkbScaledRsqrt ikb_scaled_rsqrt_constants(double d) { return IkbScaledRsqrt{d, 0.5 * d, 0.375 * d}; }
+__device__ __forceinline__ double ikb_rsqrt_times(double x, const IkbScaledRsqrt &k)
+{
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    const double t = y * y;
+    const double e = fma(-x, t, 1.0);
+    const double p = fma(e, k.d_38, k.d_half);
+    const double w = fma(e, p, k.d);
+    return y * w;
 }
 
 template <typename T>
