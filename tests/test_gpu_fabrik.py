@@ -345,3 +345,25 @@ def test_out_of_reach_split_is_value_identical(ik):
     want = c_oracle.fabrik_ikine(xyz)
     assert np.array_equal(it_whole, want["iters"])
     assert np.abs(whole - want["angles"]).max() <= TOL_F64_MODE
+
+
+@pytest.mark.parametrize("links,tol,max_iter", [([2.0, 1.5, 2.5, 1.0], 1e-3, 100), ([2.0, 2.0, 2.0, 2.0], 1e-2, 37),
+                                                ([2.0, 1.0, 1.0, 3.0], 5e-4, 64)])
+def test_split_kernel_with_other_links_and_parameters(robot, links, tol, max_iter):
+    """The out-of-reach predicate uses d1 + d2 + d3 + tol of the configured arm and max_iter of the configured solver:
+    100 000 workspace targets (split kernel) against the oracle, iteration counts exact."""
+    from inversekinematicsann_b200.kinematics.inverse import FabrikInverseKinematics
+    from oracle import c_oracle
+    rng = np.random.RandomState(31)
+    xyz = rng.rand(100_000, 3) * [6, 12, 9] + [0, -6, -3]
+    ikl = FabrikInverseKinematics(robot.dh_matrix, links, robot.effector_workspace_limits, max_err=tol,
+                                  max_iterations_num=max_iter)
+    angles, iters = ikl.ikine(xyz, as_array=True, return_iterations=True)
+    want = c_oracle.fabrik_ikine(xyz, links=np.array(links), tol=tol, max_iter=max_iter)
+    ok = want["status"] == 0
+    assert np.array_equal(iters[ok], want["iters"][ok])
+    far = np.linalg.norm(xyz - [0, 0, 2], axis=1) > sum(links[1:]) + tol + 1e-5
+    assert far.sum() > 10_000 and (iters[far] == max_iter).all()
+    finite = ok & np.isfinite(want["angles"]).all(axis=1)
+    assert np.abs(angles[finite] - want["angles"][finite]).max() <= TOL_F64_MODE
+    assert ikl.last_stats.sum_iterations == int(iters.sum())
