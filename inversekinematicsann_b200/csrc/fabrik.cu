@@ -151,10 +151,10 @@ __device__ __forceinline__ double fast_div(double a, double b)
     return fma(fma(-b, q, a), y, q);
 }
 
-__device__ __forceinline__ double dist2d(double ar, double az, double br, double bz)
+__device__ __forceinline__ double dist2d_sq(double ar, double az, double br, double bz)
 {
     const double dr = ar - br, dz = az - bz;
-    return fast_sqrt(fma(dz, dz, dr * dr));
+    return fma(dz, dz, dr * dr);
 }
 
 // round(x, 8) of reference inverse.py:81,92,100: q = rint(x * 1e8) is an integer, q / 1e8 is formed as
@@ -302,27 +302,29 @@ __device__ __forceinline__ void fabrik_epilogue(const FabrikArgs &a, int idx, in
     }
     th[0] = r3 == 0.0 ? 0.0 : (r3 != r3 ? r3 : th[0]);
     const double ab = rc.seed_ab;                                        // |AB|, A = origin: a constant
-    const double bc = dist2d(R0, Z0, r1, z1), cd = dist2d(r1, z1, r2, z2);
-    const double de = dist2d(r2, z2, r3, z3);
-    const double ac = fast_sqrt(fma(z1, z1, r1 * r1));
-    const double bd = dist2d(R0, Z0, r2, z2), ce = dist2d(r1, z1, r3, z3);
+    // Squared lengths first: only the three link lengths bc, cd, de are needed unsquared (for the denominators); the
+    // reference squares its rounded square roots again (pow(ac, 2) etc.), which differs from the squared length
+    // itself by at most 2 ulp -- the same order as this epilogue's own roots -- so the four roots of ac, bd, ce and
+    // |B t4_point_bt| are not taken at all and the "bd > dista" test of inverse.py:103 compares squares.
+    const double n_bc = dist2d_sq(R0, Z0, r1, z1), n_cd = dist2d_sq(r1, z1, r2, z2), n_de = dist2d_sq(r2, z2, r3, z3);
+    const double n_ac = fma(z1, z1, r1 * r1), n_bd = dist2d_sq(R0, Z0, r2, z2), n_ce = dist2d_sq(r1, z1, r3, z3);
+    const double bc = fast_sqrt(n_bc), cd = fast_sqrt(n_cd), de = fast_sqrt(n_de);
     double den = 2 * ab * bc;
     zero_div |= (den == 0.0);
-    const double c2 = round8(fast_div(fma(-ac, ac, fma(bc, bc, ab * ab)), den));   // inverse.py:77-81
+    const double c2 = round8(fast_div((ab * ab + n_bc) - n_ac, den));   // inverse.py:77-81
     const double acos2 = acos_fast(c2);
     th[1] = ((r1 * ux) * (r2 * ux) < 0) ? (3 * PI / 2) - acos2 : -(PI / 2 - acos2);  // :82-85
     den = 2 * bc * cd;
     zero_div |= (den == 0.0);
-    const double c3 = round8(fast_div(fma(-bd, bd, fma(cd, cd, bc * bc)), den));   // :90-92
-    th[2] = -(PI - acos_fast(c3));                                            // :93
+    const double c3 = round8(fast_div((n_bc + n_cd) - n_bd, den));      // :90-92
+    th[2] = -(PI - acos_fast(c3));                                       // :93
     den = 2 * cd * de;
-    zero_div |= (den == 0.0) | (ce == 0.0);
-    const double c4 = round8(fast_div(fma(-ce, ce, fma(de, de, cd * cd)), den));   // :98-100
+    zero_div |= (den == 0.0) | (n_ce == 0.0);
+    const double c4 = round8(fast_div((n_cd + n_de) - n_ce, den));      // :98-100
     const double acos4 = acos_fast(c4);
     // t4_point_bt = PB(C, E, |CE| / 2) (inverse.py:102): (|CE|/2)/|CE| is exactly 0.5
     const double mr = fma(0.5, r3 - r1, r1), mz = fma(0.5, z3 - z1, z1);
-    const double dista = dist2d(R0, Z0, mr, mz);
-    th[3] = (bd > dista) ? -(PI - acos4) : (PI - acos4);                 // :103-108
+    th[3] = (n_bd > dist2d_sq(R0, Z0, mr, mz)) ? -(PI - acos4) : (PI - acos4);   // :103-108
     zero_div &= finite_in;
     const bool domain = !zero_div & (fabs(c2) > 1.0 | fabs(c3) > 1.0 | fabs(c4) > 1.0);
     if (zero_div) {
