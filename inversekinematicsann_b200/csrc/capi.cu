@@ -305,6 +305,8 @@ int ikb_engine_create(const ikb_config *cfg, ikb_engine **out)
         if (status != 0)
             rc.planar = 0;
         rc.seed_ab = std::sqrt(rc.seed_r[0] * rc.seed_r[0] + rc.seed_z[0] * rc.seed_z[0]);
+        rc.seed_ab2 = rc.seed_ab * rc.seed_ab;
+        rc.half_inv_ab = 0.5 / rc.seed_ab;
     }
     *out = e;
     return IKB_OK;

@@ -138,19 +138,6 @@ __device__ __forceinline__ double fast_sqrt(double x)
     return x == 0.0 ? 0.0 : s;
 }
 
-// a / b: MUFU.RCP64H seed, two Newton steps, one residual correction (faithful to ~1 ulp)
-__device__ __forceinline__ double fast_div(double a, double b)
-{
-    double y;
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(b));
-    double e = fma(-b, y, 1.0);
-    y = fma(y, e, y);
-    e = fma(-b, y, 1.0);
-    y = fma(y, e, y);
-    const double q = a * y;
-    return fma(fma(-b, q, a), y, q);
-}
-
 __device__ __forceinline__ double dist2d_sq(double ar, double az, double br, double bz)
 {
     const double dr = ar - br, dz = az - bz;
@@ -302,25 +289,26 @@ __device__ __forceinline__ void fabrik_epilogue(const FabrikArgs &a, int idx, in
     }
     th[0] = r3 == 0.0 ? 0.0 : (r3 != r3 ? r3 : th[0]);
     const double ab = rc.seed_ab;                                        // |AB|, A = origin: a constant
-    // Squared lengths first: only the three link lengths bc, cd, de are needed unsquared (for the denominators); the
-    // reference squares its rounded square roots again (pow(ac, 2) etc.), which differs from the squared length
-    // itself by at most 2 ulp -- the same order as this epilogue's own roots -- so the four roots of ac, bd, ce and
-    // |B t4_point_bt| are not taken at all and the "bd > dista" test of inverse.py:103 compares squares.
+    // Everything on squared lengths: the reference takes seven roots, squares six of them again (pow(ac, 2) etc.)
+    // and divides by products of three; a squared rounded root differs from the squared length by at most 2 ulp --
+    // the order of this epilogue's own rounding -- so no root is taken except inside the three cosines' rsqrt, and the
+    // "bd > dista" test of inverse.py:103 compares squares.
     const double n_bc = dist2d_sq(R0, Z0, r1, z1), n_cd = dist2d_sq(r1, z1, r2, z2), n_de = dist2d_sq(r2, z2, r3, z3);
     const double n_ac = fma(z1, z1, r1 * r1), n_bd = dist2d_sq(R0, Z0, r2, z2), n_ce = dist2d_sq(r1, z1, r3, z3);
-    const double bc = fast_sqrt(n_bc), cd = fast_sqrt(n_cd), de = fast_sqrt(n_de);
-    double den = 2 * ab * bc;
-    zero_div |= (den == 0.0);
-    const double c2 = round8(fast_div((ab * ab + n_bc) - n_ac, den));   // inverse.py:77-81
+    // cos = numerator / (2 |.| |.|) = numerator * rsqrt(product of the squared lengths) / 2: one reciprocal square
+    // root per angle instead of two roots and a division (|AB| is a constant of the arm)
+    double den2 = n_bc;
+    zero_div |= (den2 == 0.0) | (ab == 0.0);
+    const double c2 = round8(((rc.seed_ab2 + n_bc) - n_ac) * ikb_rsqrt(den2) * rc.half_inv_ab);   // inverse.py:77-81
     const double acos2 = acos_fast(c2);
     th[1] = ((r1 * ux) * (r2 * ux) < 0) ? (3 * PI / 2) - acos2 : -(PI / 2 - acos2);  // :82-85
-    den = 2 * bc * cd;
-    zero_div |= (den == 0.0);
-    const double c3 = round8(fast_div((n_bc + n_cd) - n_bd, den));      // :90-92
-    th[2] = -(PI - acos_fast(c3));                                       // :93
-    den = 2 * cd * de;
-    zero_div |= (den == 0.0) | (n_ce == 0.0);
-    const double c4 = round8(fast_div((n_cd + n_de) - n_ce, den));      // :98-100
+    den2 = n_bc * n_cd;
+    zero_div |= (den2 == 0.0);
+    const double c3 = round8(((n_bc + n_cd) - n_bd) * ikb_rsqrt(den2) * 0.5);            // :90-92
+    th[2] = -(PI - acos_fast(c3));                                                        // :93
+    den2 = n_cd * n_de;
+    zero_div |= (den2 == 0.0) | (n_ce == 0.0);
+    const double c4 = round8(((n_cd + n_de) - n_ce) * ikb_rsqrt(den2) * 0.5);            // :98-100
     const double acos4 = acos_fast(c4);
     // t4_point_bt = PB(C, E, |CE| / 2) (inverse.py:102): (|CE|/2)/|CE| is exactly 0.5
     const double mr = fma(0.5, r3 - r1, r1), mz = fma(0.5, z3 - z1, z1);

@@ -25,6 +25,7 @@ struct IkbRobot {
     double seed_r[4], seed_z[4];
     double seed_xyz[12];  // the theta_1 = 0 chain in 3-D (generic path)
     double seed_ab;       // distance origin -> first joint (|AB| of inverse.py:68)
+    double seed_ab2, half_inv_ab;  // |AB|^2 and 1 / (2 |AB|) for the cosine of inverse.py:77-81
     double links[4];      // joints_distances
     double limits[6];     // xlo, xhi, ylo, yhi, zlo, zhi
     double tol;
