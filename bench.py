@@ -375,7 +375,11 @@ def main():
         W, b = ann.ann.model.kernels, ann.ann.model.biases
         aeng = ann.ann._ensure_uploaded()
         an = args.ann_rows
-        axyz = device_points(an, WORKSPACE_BOX, 4321 + rank)
+        # configs[1]: random_dist points = position_generator.random_distribution(n, limits, 'normal', std_dev=0.5)
+        # (per-axis truncated normal around 0 inside the workspace box), generated on the device (csrc/generators.cu)
+        from inversekinematicsann_b200.robot.position_generator import TrainingDataGenerator as Gen
+        axyz = Gen.random_distribution_device(an, R.effector_workspace_limits, 'normal', 0.5, seed=4321 + rank,
+                                              device=local_rank)
         aout = torch.empty(an, 4, device=dev, dtype=torch.float32)
         a_steps = max(2, min(args.steps, 5))
         bf16_peak = json.load(open(peaks_path)).get("bf16_tflops", 1590.0) if os.path.exists(peaks_path) else 1590.0
@@ -421,6 +425,8 @@ def main():
         ann_block = {
             "metric": "IK solves/sec (ANN 3->12x500 tanh->4, fused scaler+MLP+scaler)", "value": an * world / tc_s,
             "unit": UNIT, "rows_per_gpu": an, "ms_per_step": tc_s * 1e3, "dtype": "f16x2-split inputs, f32 accumulate",
+            "workload": "BASELINE configs[1]: 1M random_dist points (truncated normal, std 0.5, workspace limits) per GPU, "
+                        "float32 [n,3] in HBM -> float32 [n,4]",
             "mode": "IKB_MLP_FP16X3_TS: tcgen05 kind::f16, hi/lo split of activations and weights, x_hi as TMEM A operand, fp32 accumulators in TMEM",
             "weights": weights_note, "fk_error": ann_fk,
             "e2e": {"value": an * world * a_steps / ae2e, "unit": UNIT, "h2d_bytes_per_step": an * 12 * world,
