@@ -217,10 +217,12 @@ def main():
     n = args.rows
 
     def device_points(rows, box, seed):
-        g = torch.Generator(device=dev).manual_seed(seed)
-        u = torch.rand(rows, 3, device=dev, generator=g, dtype=torch.float32)
+        """cube_random (position_generator.py:48-55: start + len * U[0,1) per axis) generated on the device by
+        csrc/generators.cu (Philox4x32-10), `rows` points."""
+        from inversekinematicsann_b200.robot.position_generator import TrainingDataGenerator as Gen
         ln, st = box
-        return u.mul_(torch.tensor(ln, device=dev)).add_(torch.tensor(st, device=dev))
+        return Gen.cube_random_device(ln[0] * ln[1] * ln[2] / rows, ln[0], ln[1], ln[2], start=st, seed=seed,
+                                      no_of_samples=rows, device=local_rank)
 
     def timed_device_loop(fn, steps, warmup):
         """K steps bracketed by barrier + synchronize, CUDA events on torch's current stream (the stream
@@ -514,7 +516,7 @@ def main():
             "warmup": args.warmup, "ms_per_step": secs / args.steps * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": "BASELINE configs[2]: FABRIK on 100M cube_random targets per GPU, full workspace box "
-                                   "(0,-6,-3)+(6,12,9), torch Philox seed 1234+rank; configs[1] (ANN with the shipped .h5) "
+                                   "(0,-6,-3)+(6,12,9), cube_random from the device generator (Philox4x32-10, seed 1234+rank); configs[1] (ANN with the shipped .h5) "
                                    "cannot run as stated because the weights are absent -- see \"ann\"",
                        "rows_per_gpu": n, "input": "float32 [n,3] AoS in HBM (1.2 GB per GPU, > 126 MB L2: no flush needed)",
                        "output": "float32 [n,4]", "fabrik_precision": "fp64 iterate + fp64 angle extraction",

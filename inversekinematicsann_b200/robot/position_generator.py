@@ -63,8 +63,10 @@ class TrainingDataGenerator:
         return _generate(GEN_CUBE, [step, len_x, len_y, len_z, start[0], start[1], start[2], nx, ny], nx * ny * nz, **kw)
 
     @staticmethod
-    def cube_random_device(step, len_x, len_y, len_z, start=(0, 0, 0), seed=1234, **kw):
-        n = _arange_len(len_x * len_y * len_z, step)
+    def cube_random_device(step, len_x, len_y, len_z, start=(0, 0, 0), seed=1234, no_of_samples=None, **kw):
+        """`no_of_samples` overrides the reference's count len(arange(0, volume, step)) (position_generator.py:50),
+        whose floating-point step arithmetic is awkward for an exact 1e8."""
+        n = _arange_len(len_x * len_y * len_z, step) if no_of_samples is None else int(no_of_samples)
         return _generate(GEN_CUBE_RANDOM, [len_x, len_y, len_z, start[0], start[1], start[2]], n, seed=seed, **kw)
 
     @staticmethod
