@@ -87,6 +87,12 @@ class ClockSampler:
                 "power_w_max": max(float(r[2]) for r in rows), "samples": len(rows), "reasons": reasons}
 
 
+# the same string in both arms' config (the reference arm solves a bounded sample of it per step)
+WORKLOAD = ("BASELINE configs[2]: FABRIK on 100M cube_random targets per GPU, full workspace box (0,-6,-3)+(6,12,9) "
+            "(GPU arm: device generator, Philox4x32-10, seed 1234+rank); configs[1] (ANN with the shipped .h5) cannot "
+            "run as stated because the weights are absent -- see \"ann\"")
+
+
 # ---- CPU arm (oracle port) -----------------------------------------------------------------------------
 def host_points(n, box, seed):
     rng = np.random.RandomState(seed)
@@ -146,8 +152,9 @@ def run_reference_arm(args, rank):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic", "gpu_launches": 0,
-        "config": {"workload": "fabrik cube_random full workspace box (0,-6,-3)+(6,12,9), seed 1234",
-                   "rows_per_step": sample, "mean_iterations": iters},
+        "config": {"workload": WORKLOAD, "rows_per_step": sample, "mean_iterations": iters,
+                   "input": "float64 [n,3] host array (NumPy RandomState 1234: the bounded CPU sample of the same box)",
+                   "fabrik_precision": "fp64 (C restatement of the reference's Python floats)"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
                          "sample": f"{sample} targets per step x {args.steps} steps, oracle/ik_oracle.c "
                                    f"(C restatement of fabrik.py + inverse.py, OpenMP); the reference is "
@@ -515,9 +522,7 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": secs / args.steps * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "BASELINE configs[2]: FABRIK on 100M cube_random targets per GPU, full workspace box "
-                                   "(0,-6,-3)+(6,12,9), cube_random from the device generator (Philox4x32-10, seed 1234+rank); configs[1] (ANN with the shipped .h5) "
-                                   "cannot run as stated because the weights are absent -- see \"ann\"",
+            "config": {"workload": WORKLOAD,
                        "rows_per_gpu": n, "input": "float32 [n,3] AoS in HBM (1.2 GB per GPU, > 126 MB L2: no flush needed)",
                        "output": "float32 [n,4]", "fabrik_precision": "fp64 iterate + fp64 angle extraction",
                        "mean_iterations": total.sum_iterations / (n * world),
