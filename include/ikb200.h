@@ -22,12 +22,16 @@
  *   - The reference's whole-batch exception semantics (inverse.py:117: check_limits raises before
  *     any solve) map to stats.first_out_of_limits >= 0: the caller must then discard the outputs
  *     and raise OutOfRobotReachException for that row.
+ *   - Row counts: every kernel indexes rows with 64-bit integers except K1 (FABRIK), whose shared-memory queues
+ *     hold 32-bit row numbers: ikb_fabrik_solve_device refuses n >= 2^31 per call (the *_host entry points chunk
+ *     internally and have no limit).
  *   - There is no CPU fallback: without a CUDA device every compute entry point fails with
  *     IKB_ERR_CUDA.
  */
 #ifndef IKB200_H
 #define IKB200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -177,12 +181,31 @@ int ikb_ann_solve_host(ikb_engine *e, const void *xyz, int xyz_dtype, int64_t n,
 int ikb_generate_device(ikb_engine *e, int kind, const double *params, int n_params, int64_t n, int64_t row_offset,
                         void *xyz_out, int xyz_dtype, uint64_t seed, void *stream);
 
+/* ---- pinned host buffers ------------------------------------------------------------------------
+ * The reference hands results back as freshly built Python lists (inverse.py:137,155) and the broker serialises
+ * them into a new message body (rpc_broker.py:88-99).  At 1e7+ rows the allocation and the pageable copy of
+ * that buffer cost more than the solve, so the array-native callers (ikine(out=...), the IKB1 broker reply) write
+ * into page-locked memory obtained here: allocated by the calling thread on the engine's device context
+ * (cudaHostAlloc, default flags: not portable, NUMA placement follows the caller's CPU affinity).
+ * ikb_host_register page-locks an existing buffer (e.g. a received request body) for the duration of one call. */
+int ikb_host_alloc(ikb_engine *e, size_t bytes, void **out);
+int ikb_host_free(ikb_engine *e, void *p);
+int ikb_host_register(ikb_engine *e, void *p, size_t bytes, int read_only);
+int ikb_host_unregister(ikb_engine *e, void *p);
+
 /* ---- measurement helpers --------------------------------------------------------------------- */
 /* dependent-FMA-chain microbenchmark on `stream`'s device: achieved TFLOP/s (2 flops per FMA) of
  * the fp32 (dtype IKB_F32) or fp64 (IKB_F64) CUDA-core pipe; the roofline denominator for FABRIK. */
 int ikb_microbench_fma(ikb_engine *e, int dtype, double *tflops_out);
 /* number of kernel launches this engine has issued since creation (bench.py's gpu_launches)     */
 int64_t ikb_launch_count(const ikb_engine *e);
+/* the *_host pipelines with the kernels removed: n rows of in_row_bytes go host -> device and n rows of
+ * out_row_bytes come back device -> host through the same staging slots, streams and chunk sizes as
+ * ikb_fabrik_solve_host / ikb_ann_solve_host.  What it takes is the copy ceiling `e2e` is measured against. */
+int ikb_copy_pipeline_host(ikb_engine *e, const void *in, int64_t in_row_bytes, int64_t n, void *out,
+                           int64_t out_row_bytes);
+/* theoretical CUDA-core peak of the engine's device in TFLOP/s: SMs x lanes (128 fp32 / 64 fp64) x 2 x max SM clock */
+int ikb_theoretical_fma_peak(ikb_engine *e, int dtype, double *tflops_out);
 
 #ifdef __cplusplus
 }

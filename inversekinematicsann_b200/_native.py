@@ -24,6 +24,8 @@ EXPORTED_SYMBOLS = [
     "ikb_fk_device", "ikb_fk_host", "ikb_fk_chain_host",
     "ikb_mlp_load", "ikb_ann_solve_device", "ikb_ann_solve_host",
     "ikb_generate_device", "ikb_microbench_fma", "ikb_launch_count",
+    "ikb_host_alloc", "ikb_host_free", "ikb_host_register", "ikb_host_unregister",
+    "ikb_copy_pipeline_host", "ikb_theoretical_fma_peak",
 ]
 
 
@@ -87,6 +89,12 @@ def load():
         "ikb_generate_device": (i32, [engine, i32, vp, i32, i64, i64, vp, i32, ctypes.c_uint64, vp]),
         "ikb_microbench_fma": (i32, [engine, i32, ctypes.POINTER(dbl)]),
         "ikb_launch_count": (i64, [engine]),
+        "ikb_host_alloc": (i32, [engine, ctypes.c_size_t, ctypes.POINTER(vp)]),
+        "ikb_host_free": (i32, [engine, vp]),
+        "ikb_host_register": (i32, [engine, vp, ctypes.c_size_t, i32]),
+        "ikb_host_unregister": (i32, [engine, vp]),
+        "ikb_copy_pipeline_host": (i32, [engine, vp, i64, i64, vp, i64]),
+        "ikb_theoretical_fma_peak": (i32, [engine, i32, ctypes.POINTER(dbl)]),
     }
     for name, (res, args) in protos.items():
         try:

@@ -651,7 +651,86 @@ int ikb_generate_device(ikb_engine *e, int kind, const double *params, int n_par
     return IKB_OK;
 }
 
+// ---- pinned host buffers --------------------------------------------------------------------------
+int ikb_host_alloc(ikb_engine *e, size_t bytes, void **out)
+{
+    if (!e || !out || bytes == 0)
+        return fail(e, IKB_ERR_INVALID, "ikb_host_alloc: bad argument");
+    *out = nullptr;
+    IKB_CUDA(e, cudaSetDevice(e->device));
+    IKB_CUDA(e, cudaHostAlloc(out, bytes, cudaHostAllocDefault));
+    return IKB_OK;
+}
+
+int ikb_host_free(ikb_engine *e, void *p)
+{
+    if (!e)
+        return IKB_ERR_INVALID;
+    if (!p)
+        return IKB_OK;
+    IKB_CUDA(e, cudaSetDevice(e->device));
+    IKB_CUDA(e, cudaFreeHost(p));
+    return IKB_OK;
+}
+
+int ikb_host_register(ikb_engine *e, void *p, size_t bytes, int read_only)
+{
+    if (!e || !p || bytes == 0)
+        return fail(e, IKB_ERR_INVALID, "ikb_host_register: bad argument");
+    IKB_CUDA(e, cudaSetDevice(e->device));
+    cudaError_t err = cudaHostRegister(p, bytes, read_only ? cudaHostRegisterReadOnly : cudaHostRegisterDefault);
+    if (err != cudaSuccess && read_only) {  // read-only registration is optional on some platforms
+        (void)cudaGetLastError();
+        err = cudaHostRegister(p, bytes, cudaHostRegisterDefault);
+    }
+    IKB_CUDA(e, err);
+    return IKB_OK;
+}
+
+int ikb_host_unregister(ikb_engine *e, void *p)
+{
+    if (!e || !p)
+        return fail(e, IKB_ERR_INVALID, "ikb_host_unregister: bad argument");
+    IKB_CUDA(e, cudaSetDevice(e->device));
+    IKB_CUDA(e, cudaHostUnregister(p));
+    return IKB_OK;
+}
+
 // ---- measurement ----------------------------------------------------------------------------------
+int ikb_copy_pipeline_host(ikb_engine *e, const void *in, int64_t in_row_bytes, int64_t n, void *out,
+                           int64_t out_row_bytes)
+{
+    if (!e || n < 0 || in_row_bytes < 0 || out_row_bytes < 0 || in_row_bytes > 32 || out_row_bytes > 32 ||
+        (n > 0 && ((in_row_bytes && !in) || (out_row_bytes && !out))))
+        return fail(e, IKB_ERR_INVALID, "ikb_copy_pipeline_host: bad argument (rows of at most 32 bytes)");
+    int rc = host_begin(e, n);
+    if (rc)
+        return rc;
+    int it = 0;
+    for (long long lo = 0, m = 0; lo < n; lo += m, ++it) {
+        Slot &s = e->slots[it % kSlots];
+        m = host_chunk_rows(lo, n);
+        if (in_row_bytes)
+            IKB_CUDA(e, cudaMemcpyAsync(s.d_in, (const char *)in + lo * in_row_bytes, m * in_row_bytes,
+                                        cudaMemcpyHostToDevice, s.stream));
+        if (out_row_bytes)
+            IKB_CUDA(e, cudaMemcpyAsync((char *)out + lo * out_row_bytes, s.d_out, m * out_row_bytes,
+                                        cudaMemcpyDeviceToHost, s.stream));
+    }
+    return host_end(e, nullptr);
+}
+
+int ikb_theoretical_fma_peak(ikb_engine *e, int dtype, double *tflops_out)
+{
+    if (!e || !tflops_out || bad_dtype(dtype))
+        return fail(e, IKB_ERR_INVALID, "ikb_theoretical_fma_peak: bad argument");
+    int khz = 0;
+    IKB_CUDA(e, cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, e->device));
+    const double lanes = dtype == IKB_F64 ? 64.0 : 128.0;  // sm_100: 128 fp32 / 64 fp64 FMA lanes per SM
+    *tflops_out = e->num_sms * lanes * 2.0 * (double)khz * 1e3 / 1e12;
+    return IKB_OK;
+}
+
 int ikb_microbench_fma(ikb_engine *e, int dtype, double *tflops_out)
 {
     if (!e || !tflops_out || bad_dtype(dtype))

@@ -145,6 +145,23 @@ class IkEngine:
             raise ValueError(f"{what} must have shape (n, {cols}), got {a.shape}")
         return a
 
+    @staticmethod
+    def _check_out(out, n, cols, dtypes, what):
+        """A caller-supplied result buffer goes to the C ABI as a raw pointer: refuse anything the library would
+        write past or into the wrong places (wrong shape, strided view, read-only, unexpected dtype)."""
+        if not isinstance(out, np.ndarray):
+            raise TypeError(f"{what} must be a numpy.ndarray, not {type(out).__name__}")
+        want = (n, cols) if cols else (n,)
+        if out.shape != want:
+            raise ValueError(f"{what} must have shape {want}, got {out.shape}")
+        if out.dtype not in dtypes:
+            raise TypeError(f"{what} must have dtype {' or '.join(np.dtype(d).name for d in dtypes)}, got {out.dtype}")
+        if not out.flags.c_contiguous:
+            raise ValueError(f"{what} must be C-contiguous")
+        if not out.flags.writeable:
+            raise ValueError(f"{what} is read-only")
+        return out
+
     def check_limits(self, xyz):
         """reference inverse.py:26-35 -> index of the first out-of-box row or -1."""
         xyz = self._rows(xyz, 3, "points")
@@ -162,6 +179,7 @@ class IkEngine:
         n = xyz.shape[0]
         if out is None:
             out = np.empty((n, 4), dtype=out_dtype)
+        self._check_out(out, n, 4, (np.float32, np.float64), "out")
         iters = np.empty(n, dtype=np.int32) if return_iters else None
         fk_err = np.empty(n, dtype=out.dtype) if return_fk_error else None
         s = _native.IkbStats()
@@ -251,6 +269,7 @@ class IkEngine:
         n = xyz.shape[0]
         if out is None:
             out = np.empty((n, 4), dtype=np.float32)
+        self._check_out(out, n, 4, (np.float32,), "out")  # Keras / sklearn return float32 (ann.py:70-76)
         fk_err = np.empty(n, dtype=np.float32) if return_fk_error else None
         s = _native.IkbStats()
         self._check(self._lib.ikb_ann_solve_host(self._handle, xyz.ctypes.data, _np_dtype_code(xyz), n,
@@ -265,6 +284,37 @@ class IkEngine:
         self._check(self._lib.ikb_microbench_fma(self._handle, code, ctypes.byref(out)), "ikb_microbench_fma")
         return float(out.value)
 
+    def theoretical_fma_peak(self, dtype="f64"):
+        """SMs x FMA lanes x 2 x max SM clock, in TFLOP/s (the number the live microbenchmark is checked against)."""
+        out = ctypes.c_double(0.0)
+        code = _native.IKB_F64 if dtype == "f64" else _native.IKB_F32
+        self._check(self._lib.ikb_theoretical_fma_peak(self._handle, code, ctypes.byref(out)), "ikb_theoretical_fma_peak")
+        return float(out.value)
+
+    # ---- pinned host buffers ----------------------------------------------------------------------
+    def pinned_buffer(self, nbytes):
+        """Page-locked host memory from the library (cudaHostAlloc by this thread on this engine's device)."""
+        return PinnedBuffer(self, nbytes)
+
+    def pinned_empty(self, shape, dtype=np.float32):
+        """An ndarray in page-locked memory: what `ikine(..., out=)` wants for large trajectories."""
+        shape = tuple(int(v) for v in (shape if isinstance(shape, (tuple, list)) else (shape,)))
+        nbytes = max(1, int(np.prod(shape)) * np.dtype(dtype).itemsize)
+        return self.pinned_buffer(nbytes).array(dtype, shape)
+
+    def copy_pipeline(self, src, dst):
+        """The host pipeline of the solve calls with the kernels removed (bench.py's copy ceiling): `src` rows go
+        to the device, `dst` rows come back; both are (n, c) arrays of at most 32 bytes per row."""
+        n = src.shape[0] if src is not None else dst.shape[0]
+        for a in (src, dst):
+            if a is not None and (a.shape[0] != n or not a.flags.c_contiguous):
+                raise ValueError("src and dst must be C-contiguous with the same number of rows")
+        self._check(self._lib.ikb_copy_pipeline_host(
+            self._handle, src.ctypes.data if src is not None else None,
+            src.strides[0] if src is not None else 0, n,
+            dst.ctypes.data if dst is not None else None, dst.strides[0] if dst is not None else 0),
+            "ikb_copy_pipeline_host")
+
     # ---- device-buffer entry points (torch CUDA tensors; async on torch's current stream) ---------
     def _dev_rows(self, t, cols, what):
         if not _is_torch_tensor(t) or not t.is_cuda:
@@ -275,11 +325,26 @@ class IkEngine:
             raise ValueError(f"{what} must be a contiguous (n, {cols}) tensor")
         return t
 
+    @staticmethod
+    def _same_rows(a, b, what):
+        if a.shape[0] != b.shape[0]:
+            raise ValueError(f"{what} has {b.shape[0]} rows for {a.shape[0]} points")
+
+    def _dev_vec(self, t, n, dtype, what):
+        if not _is_torch_tensor(t) or not t.is_cuda or t.device.index != self.device:
+            raise TypeError(f"{what} must be a CUDA torch tensor on cuda:{self.device}")
+        if str(t.dtype) != dtype or t.numel() != n or not t.is_contiguous():
+            raise ValueError(f"{what} must be a contiguous {dtype} tensor with {n} elements")
+        return t
+
     def fabrik_solve_device(self, xyz, out, iters=None, precision="f64", fk_err=None, fk_stats=False):
         xyz = self._dev_rows(xyz, 3, "points")
         out = self._dev_rows(out, 4, "angles")
-        if fk_err is not None and (fk_err.dtype != out.dtype or fk_err.numel() != out.shape[0]):
-            raise ValueError("fk_err must have the angles' dtype and one value per row")
+        self._same_rows(xyz, out, "angles")
+        if iters is not None:
+            self._dev_vec(iters, xyz.shape[0], "torch.int32", "iters")
+        if fk_err is not None:
+            self._dev_vec(fk_err, xyz.shape[0], str(out.dtype), "fk_err")
         prec = {"f64": _native.IKB_FABRIK_F64, "f32": _native.IKB_FABRIK_F32}[precision]
         self._check(self._lib.ikb_fabrik_solve_device(
             self._handle, xyz.data_ptr(), _torch_dtype_code(xyz), xyz.shape[0], out.data_ptr(),
@@ -290,8 +355,11 @@ class IkEngine:
     def ann_solve_device(self, xyz, out, mode="fp32", fk_err=None, fk_stats=False):
         xyz = self._dev_rows(xyz, 3, "points")
         out = self._dev_rows(out, 4, "angles")
-        if fk_err is not None and (str(fk_err.dtype) != "torch.float32" or fk_err.numel() != out.shape[0]):
-            raise ValueError("fk_err must be float32 with one value per row")
+        self._same_rows(xyz, out, "angles")
+        if str(out.dtype) != "torch.float32":
+            raise TypeError(f"angles must be float32 (Keras / sklearn return float32), got {out.dtype}")
+        if fk_err is not None:
+            self._dev_vec(fk_err, xyz.shape[0], "torch.float32", "fk_err")
         self._check(self._lib.ikb_ann_solve_device(
             self._handle, xyz.data_ptr(), _torch_dtype_code(xyz), xyz.shape[0], out.data_ptr(),
             fk_err.data_ptr() if fk_err is not None else None, int(bool(fk_stats)),
@@ -299,6 +367,17 @@ class IkEngine:
 
     def fk_device(self, angles, targets=None, pos=None, err=None):
         angles = self._dev_rows(angles, 4, "angles")
+        n = angles.shape[0]
+        if targets is not None:
+            self._same_rows(angles, self._dev_rows(targets, 3, "targets"), "targets")
+        if pos is not None:
+            self._same_rows(angles, self._dev_rows(pos, 3, "pos"), "pos")
+            if pos.dtype != angles.dtype:
+                raise TypeError("pos must have the angles' dtype")
+        if err is not None:
+            if targets is None:
+                raise ValueError("err needs targets")
+            self._dev_vec(err, n, str(angles.dtype), "err")
         self._check(self._lib.ikb_fk_device(
             self._handle, angles.data_ptr(), _torch_dtype_code(angles), angles.shape[0],
             pos.data_ptr() if pos is not None else None,
@@ -317,6 +396,42 @@ class IkEngine:
 
     def stats_reset_torch(self):
         self.stats_reset(_torch_stream_ptr(self.device))
+
+
+class PinnedBuffer:
+    """nbytes of page-locked host memory owned by libikb200 (ikb_host_alloc / ikb_host_free).  Views handed out by
+    `array()` / `view()` keep the buffer alive; it is freed when the last of them is gone."""
+
+    def __init__(self, engine, nbytes):
+        self._engine, self.nbytes = engine, int(nbytes)
+        ptr = ctypes.c_void_p()
+        engine._check(engine._lib.ikb_host_alloc(engine._handle, self.nbytes, ctypes.byref(ptr)), "ikb_host_alloc")
+        self.ptr = ptr.value
+        raw = (ctypes.c_ubyte * self.nbytes).from_address(self.ptr)
+        raw._ikb_owner = self            # every NumPy view's base chain ends at `raw`
+        self._bytes = np.frombuffer(raw, dtype=np.uint8)
+
+    def array(self, dtype, shape, offset=0):
+        dtype = np.dtype(dtype)
+        count = int(np.prod(shape))
+        if offset < 0 or offset + count * dtype.itemsize > self.nbytes:
+            raise ValueError("view exceeds the pinned buffer")
+        return self._bytes[offset: offset + count * dtype.itemsize].view(dtype).reshape(shape)
+
+    def view(self, offset=0, nbytes=None):
+        nbytes = self.nbytes - offset if nbytes is None else nbytes
+        return memoryview(self._bytes[offset: offset + nbytes])
+
+    def close(self):
+        if getattr(self, "ptr", None) and getattr(self._engine, "_handle", None) and self._engine._handle.value:
+            self._engine._lib.ikb_host_free(self._engine._handle, self.ptr)
+        self.ptr = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 _MLP_MODES = {"fp32": _native.IKB_MLP_FP32_SIMT, "fp16x3": _native.IKB_MLP_FP16X3_TC,

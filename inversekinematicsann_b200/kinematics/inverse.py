@@ -61,7 +61,7 @@ class InverseKinematics(ABC):
         rows = [(r, kind) for r, kind in ((stats.first_zero_division, ZeroDivisionError),
                                           (stats.first_domain_error, ValueError)) if r >= 0]
         if rows:
-            _, kind = min(rows)
+            _, kind = min(rows, key=lambda t: t[0])  # same row in both classes: the division comes first upstream
             raise kind('float division by zero' if kind is ZeroDivisionError else 'math domain error')
 
     @abstractmethod

@@ -53,34 +53,51 @@ def reduce_stats(stats, row_offset=0, device=None):
     return out
 
 
-def gather_rows(local_rows, n_total, dst=0):
+def gather_rows(local_rows, n_total, dst=0, out=None):
     """Gather contiguous row shards (torch tensors, (n_local, c)) to rank `dst` in trajectory order.
-    Returns the (n_total, c) tensor on `dst` and None elsewhere.  Shards may differ by one row, so
-    they are padded to the largest shard for all_gather_into_tensor."""
+    Returns the (n_total, c) tensor on `dst` and None elsewhere.  Point-to-point: every other rank sends its shard
+    once and `dst` receives each shard straight into its slice of the result (shards may differ by one row; nobody
+    but `dst` allocates or receives anything -- the final gather SURVEY 8e describes, not an all-gather).
+    `out` (on `dst`): a preallocated (n_total, c) tensor to receive into."""
     if not _dist_ready() or dist.get_world_size() == 1:
         return local_rows
     world, rank = dist.get_world_size(), dist.get_rank()
     sizes = [shard_range(n_total, r, world) for r in range(world)]
-    biggest = max(hi - lo for lo, hi in sizes)
-    padded = local_rows
-    if local_rows.shape[0] < biggest:
-        pad = torch.zeros((biggest - local_rows.shape[0],) + tuple(local_rows.shape[1:]),
-                          dtype=local_rows.dtype, device=local_rows.device)
-        padded = torch.cat([local_rows, pad], dim=0)
-    out = torch.empty((world * biggest,) + tuple(local_rows.shape[1:]), dtype=local_rows.dtype,
-                      device=local_rows.device)
-    dist.all_gather_into_tensor(out, padded.contiguous())
-    if rank != dst:
-        return None
-    parts = [out[r * biggest: r * biggest + (hi - lo)] for r, (lo, hi) in enumerate(sizes)]
-    return torch.cat(parts, dim=0)
+    local_rows = local_rows.contiguous()
+    ops, full = [], None
+    if rank == dst:
+        shape = (int(n_total),) + tuple(local_rows.shape[1:])
+        full = out if out is not None else torch.empty(shape, dtype=local_rows.dtype, device=local_rows.device)
+        if tuple(full.shape) != shape or full.dtype != local_rows.dtype or not full.is_contiguous():
+            raise ValueError(f"out must be a contiguous {shape} tensor of {local_rows.dtype}")
+        lo, hi = sizes[dst]
+        full[lo:hi].copy_(local_rows)
+        ops = [dist.P2POp(dist.irecv, full[lo:hi], r) for r, (lo, hi) in enumerate(sizes) if r != dst and hi > lo]
+    elif local_rows.shape[0] > 0:
+        ops = [dist.P2POp(dist.isend, local_rows, dst)]
+    if ops:
+        for work in dist.batch_isend_irecv(ops):
+            work.wait()
+    return full
+
+
+def chunk_ranges(n, chunk_rows):
+    """[lo, hi) pieces of a shard of n rows, the grid both ends of the chunked gather agree on."""
+    return [(lo, min(lo + chunk_rows, n)) for lo in range(0, n, chunk_rows)]
 
 
 class _ShardedIkine:
-    """Every rank passes the SAME full trajectory (as the reference's caller would), solves only its contiguous
-    range on its own GPU, and rank 0 gets the full (n, 4) result; the reference's exceptions are raised on every
-    rank from the reduced diagnostics.  With `fk_error=True` the per-rank error sums are all-reduced as well
-    (BASELINE config 4: the FK round trip of every prediction), available as `ik.last_stats.mean_fk_error`."""
+    """The reference scales by running several brokers and letting the user split the data set (README.md:11,
+    rpc_broker.py:65-68); here one torchrun job owns the whole trajectory, one contiguous row range per GPU.
+
+    `ikine(points)`: every rank passes the SAME full host trajectory (as the reference's caller would), solves only
+    its range on its own GPU, and rank `dst` gets the full (n, 4) result; the reference's exceptions are raised on
+    every rank from the reduced diagnostics.  With `fk_error=True` the per-rank error sums are all-reduced as well
+    (BASELINE config 4: the FK round trip of every prediction), available as `ik.last_stats.mean_fk_error`.
+
+    `ikine_device(xyz_shard, ...)`: the device-resident form -- each rank holds only ITS rows in HBM, nothing
+    touches the host, and the optional gather ships finished chunks to `gather_dst` over NCCL send/recv while the
+    next chunk is being solved."""
 
     def __init__(self, ik):
         self.ik = ik
@@ -88,39 +105,135 @@ class _ShardedIkine:
     def _solve_local(self, eng, local, fk_error):
         raise NotImplementedError
 
-    def ikine(self, points, gather=True, fk_error=False):
+    def _solve_device(self, eng, xyz, out, fk_error):
+        raise NotImplementedError
+
+    @staticmethod
+    def _world_rank():
+        return (dist.get_world_size(), dist.get_rank()) if _dist_ready() else (1, 0)
+
+    def ikine(self, points, gather=True, fk_error=False, dst=0):
         import numpy as np
         from .kinematics._shared import points_to_array
         arr = points_to_array(points)
-        world = dist.get_world_size() if _dist_ready() else 1
-        rank = dist.get_rank() if _dist_ready() else 0
+        world, rank = self._world_rank()
         lo, hi = shard_range(arr.shape[0], rank, world)
         local = arr[lo:hi]
-        eng = self.ik._engine()
+        eng = self._engine()
         angles, stats = self._solve_local(eng, local, fk_error) if hi > lo else \
             (np.zeros((0, 4), dtype=self._out_dtype), IkStats())
         total = reduce_stats(stats, row_offset=lo)
         self.ik.last_stats = total
         self.ik._raise_from_stats(points, total)
-        if not gather:
+        if not gather or world == 1:
             return angles
         dev = f"cuda:{eng.device}" if dist.get_backend() == "nccl" else "cpu"
-        full = gather_rows(torch.from_numpy(angles).to(dev), arr.shape[0])
+        full = gather_rows(torch.from_numpy(angles).to(dev), arr.shape[0], dst=dst)
         return None if full is None else full.cpu().numpy()
+
+    def ikine_device(self, xyz_shard, out_shard=None, n_total=None, gather_dst=None, gather_out=None,
+                     chunk_rows=1 << 22, fk_error=False, check=True):
+        """Solve this rank's rows where they are.  xyz_shard: (n_local, 3) CUDA tensor = rows
+        shard_range(n_total, rank, world) of the trajectory; out_shard: optional (n_local, 4) CUDA tensor.
+        Returns out_shard, or -- with gather_dst -- the full (n_total, 4) tensor on that rank and None elsewhere.
+        `check=False` skips the diagnostics round trip (one device->host read + one all-reduce): the caller vouches
+        for the inputs and reads `eng.stats_fetch_torch()` itself."""
+        world, rank = self._world_rank()
+        eng = self._engine()
+        n_local = int(xyz_shard.shape[0])
+        if n_total is None:
+            if world > 1 and gather_dst is not None:
+                raise ValueError("n_total is required to gather (shards may differ by one row)")
+            n_total = n_local
+        lo, hi = shard_range(n_total, rank, world)
+        if hi - lo != n_local:
+            raise ValueError(f"rank {rank} of {world} owns rows [{lo}, {hi}) of {n_total}, got {n_local} rows")
+        if out_shard is None:
+            out_shard = torch.empty((n_local, 4), dtype=self._device_out_dtype(xyz_shard), device=xyz_shard.device)
+        if check:
+            eng.stats_reset_torch()
+        gathering = gather_dst is not None and world > 1
+        full, pending = None, []
+        if gathering and rank == gather_dst:
+            full = gather_out if gather_out is not None else \
+                torch.empty((n_total, 4), dtype=out_shard.dtype, device=out_shard.device)
+        sizes = [shard_range(n_total, r, world) for r in range(world)]
+        n_chunks = max(len(chunk_ranges(h - l, chunk_rows)) for l, h in sizes) if gathering else 0
+        mine = chunk_ranges(n_local, chunk_rows if gathering else max(n_local, 1))
+        for c in range(max(len(mine), n_chunks)):
+            if c < len(mine):
+                a, b = mine[c]
+                self._solve_device(eng, xyz_shard[a:b], out_shard[a:b], fk_error)
+            if not gathering:
+                continue
+            if rank == gather_dst:
+                ops = []
+                for r, (l, h) in enumerate(sizes):
+                    pieces = chunk_ranges(h - l, chunk_rows)
+                    if r != rank and c < len(pieces):
+                        ops.append(dist.P2POp(dist.irecv, full[l + pieces[c][0]: l + pieces[c][1]], r))
+                if ops:
+                    pending += dist.batch_isend_irecv(ops)
+            elif c < len(mine):
+                pending.append(dist.isend(out_shard[mine[c][0]: mine[c][1]], gather_dst))
+        if gathering and rank == gather_dst:
+            full[lo:hi].copy_(out_shard)
+        for work in pending:
+            work.wait()
+        if check:
+            total = reduce_stats(eng.stats_fetch_torch(), row_offset=lo)
+            self.ik.last_stats = total
+            self.ik._raise_from_stats(_RowPrinter(xyz_shard, lo), total)
+        if gathering:
+            return full
+        return out_shard
+
+
+class _RowPrinter:
+    """`points[i]` for the exception text when the points live in HBM on several ranks: the offending row is
+    fetched from this rank if it owns it, else described by its index."""
+
+    def __init__(self, shard, lo):
+        self.shard, self.lo = shard, lo
+
+    def __getitem__(self, i):
+        j = i - self.lo
+        if 0 <= j < self.shard.shape[0]:
+            return self.shard[j].tolist()
+        return f"#{i}"
 
 
 class ShardedFabrik(_ShardedIkine):
     """Drop-in for FabrikInverseKinematics.ikine over all ranks of a torchrun job."""
     _out_dtype = "float64"
 
+    def _engine(self):
+        return self.ik._engine()
+
+    @staticmethod
+    def _device_out_dtype(xyz):
+        return xyz.dtype
+
     def _solve_local(self, eng, local, fk_error):
         return eng.fabrik_solve(local, precision=self.ik.precision, fk_stats=fk_error)[:2]
+
+    def _solve_device(self, eng, xyz, out, fk_error):
+        eng.fabrik_solve_device(xyz, out, precision=self.ik.precision, fk_stats=fk_error)
 
 
 class ShardedAnn(_ShardedIkine):
     """Drop-in for AnnInverseKinematics.ikine over all ranks (weights replicated per GPU at load time)."""
     _out_dtype = "float32"
 
+    def _engine(self):
+        return self.ik.ann._ensure_uploaded()
+
+    @staticmethod
+    def _device_out_dtype(xyz):
+        return torch.float32
+
     def _solve_local(self, eng, local, fk_error):
-        eng = self.ik.ann._ensure_uploaded()
         return eng.ann_solve(local, mode=self.ik.ann.mode, fk_stats=fk_error)[:2]
+
+    def _solve_device(self, eng, xyz, out, fk_error):
+        eng.ann_solve_device(xyz, out, mode=self.ik.ann.mode, fk_stats=fk_error)

@@ -96,3 +96,36 @@ def test_product_and_oracle_synthetic_weights_agree():
     for name in ("SHIPPED_MEAN_X", "SHIPPED_SCALE_X", "SHIPPED_MEAN_Y", "SHIPPED_SCALE_Y"):
         assert np.array_equal(getattr(models, name), getattr(np_oracle, name))
     assert models.REFERENCE_LAYER_DIMS == np_oracle.LAYER_DIMS
+
+
+def test_out_buffer_validation_happens_before_the_c_abi():
+    """`out=` reaches libikb200 as a raw pointer: wrong shape / dtype / strides must be refused in Python."""
+    from inversekinematicsann_b200.engine import IkEngine
+    ok = np.empty((5, 4), dtype=np.float32)
+    assert IkEngine._check_out(ok, 5, 4, (np.float32, np.float64), "out") is ok
+    with pytest.raises(ValueError):
+        IkEngine._check_out(np.empty((5, 3), np.float32), 5, 4, (np.float32,), "out")      # too small
+    with pytest.raises(ValueError):
+        IkEngine._check_out(np.empty((4, 4), np.float32), 5, 4, (np.float32,), "out")      # too few rows
+    with pytest.raises(ValueError):
+        IkEngine._check_out(np.empty((5, 8), np.float32)[:, ::2], 5, 4, (np.float32,), "out")  # strided view
+    with pytest.raises(TypeError):
+        IkEngine._check_out(np.empty((5, 4), np.float64), 5, 4, (np.float32,), "out")      # ANN writes float32
+    with pytest.raises(TypeError):
+        IkEngine._check_out([[0.0] * 4] * 5, 5, 4, (np.float32,), "out")
+    ro = np.empty((5, 4), np.float32)
+    ro.flags.writeable = False
+    with pytest.raises(ValueError):
+        IkEngine._check_out(ro, 5, 4, (np.float32,), "out")
+
+
+def test_raise_from_stats_same_row_in_two_error_classes():
+    """A zero-division row and a domain-error row with the same index must not break the exception mapping."""
+    from inversekinematicsann_b200.engine import IkStats
+    from inversekinematicsann_b200.kinematics.inverse import FabrikInverseKinematics
+    from inversekinematicsann_b200.robot.robot import SixDOFRobot as R
+    ik = FabrikInverseKinematics(R.dh_matrix, R.links_lengths, R.effector_workspace_limits)
+    with pytest.raises(ZeroDivisionError):
+        ik._raise_from_stats([[0, 0, 2]] * 4, IkStats(first_zero_division=3, first_domain_error=3))
+    with pytest.raises(ValueError):
+        ik._raise_from_stats([[0, 0, 2]] * 4, IkStats(first_zero_division=3, first_domain_error=1))

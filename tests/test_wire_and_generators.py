@@ -22,13 +22,40 @@ def test_binary_codec_round_trip():
     assert reply["status"] == "OK" and np.array_equal(reply["angles"], ang)
     err = wire.decode_binary_reply(wire.encode_binary_reply(error=ValueError("boom")))
     assert err == {"status": "ERROR", "reason": "boom"}
+    # the reply names its dtype: a float64 (FABRIK) reply decodes as float64 without being told, and a body whose
+    # length disagrees with its header is refused instead of being reinterpreted
+    ang64 = np.arange(8, dtype=np.float64).reshape(2, 4)
+    back = wire.decode_binary_reply(wire.encode_binary_reply(ang64))["angles"]
+    assert back.dtype == np.float64 and np.array_equal(back, ang64)
+    assert wire.decode_binary_reply(wire.encode_binary_reply(ang))["angles"].dtype == np.float32
+    with pytest.raises(ValueError):
+        wire.decode_binary_reply(wire.encode_binary_reply(ang64)[:-8])
+    for short in (b"IKB1", b"IKB1\x00\x00", b""):
+        with pytest.raises(ValueError):
+            wire.decode_binary_reply(short)
+        with pytest.raises(ValueError):
+            wire.decode_binary_request(short)
+
+
+def test_malformed_binary_request_gets_an_error_reply():
+    """A truncated IKB1 message must not kill the consumer (upstream dies on anything it does not catch)."""
+    for body in (b"IKB1", b"IKB1\x00\x00\x00\x00\x05", wire.encode_binary_request(np.zeros((4, 3)))[:-1],
+                 b"IKB1" + (9).to_bytes(4, "little") + (0).to_bytes(8, "little")):
+        reply = wire.decode_binary_reply(wire.handle_request(_FakeEngine(), body))
+        assert reply["status"] == "ERROR" and reply["reason"]
 
 
 class _FakeEngine:
-    def ikine(self, points, as_array=False):
+    def ikine(self, points, as_array=False, out=None):
         if len(points) == 0:
             raise ZeroDivisionError("float division by zero")
         return np.zeros((len(points), 4), dtype=np.float32) if as_array else [[0.0] * 4 for _ in points]
+
+
+def test_binary_request_without_native_engine_uses_plain_reply():
+    pts = np.ones((5, 3), dtype=np.float32)
+    reply = wire.decode_binary_reply(wire.handle_request(_FakeEngine(), wire.encode_binary_request(pts)))
+    assert reply["status"] == "OK" and reply["angles"].shape == (5, 4)
 
 
 def test_handle_request_json_schema_and_errors():
@@ -49,8 +76,15 @@ def test_broker_round_trip_on_gpu():
     ik = FabrikInverseKinematics(R.dh_matrix, R.links_lengths, R.effector_workspace_limits)
     pts = np.random.default_rng(2).uniform([1, -2, 1], [3, 2, 4], size=(5000, 3))
     want = c_oracle.fabrik_ikine(pts)["angles"]
-    reply = wire.decode_binary_reply(wire.handle_request(ik, wire.encode_binary_request(pts)), dtype=np.float64)
+    reply = wire.decode_binary_reply(wire.handle_request(ik, wire.encode_binary_request(pts)))
+    assert reply["angles"].dtype == np.float64          # the reply carries the request's dtype
     np.testing.assert_allclose(reply["angles"], want, rtol=0, atol=1e-9)
+    view = wire.handle_request(ik, wire.encode_binary_request(pts.astype(np.float32)), zero_copy=True)
+    assert isinstance(view, memoryview) and len(view) == 16 + 5000 * 16
+    r32 = wire.decode_binary_reply(view)
+    assert r32["angles"].dtype == np.float32
+    want32 = c_oracle.fabrik_ikine(pts.astype(np.float32).astype(np.float64))["angles"]
+    np.testing.assert_allclose(r32["angles"], want32, rtol=0, atol=2e-6)
     js = json.loads(wire.handle_request(ik, json.dumps({"positions": pts[:20].tolist()}).encode()))
     np.testing.assert_allclose(js["angles"], want[:20], rtol=0, atol=1e-9)
     out = json.loads(wire.handle_request(ik, json.dumps({"positions": [[1, 2, 3], [1, 2, 7]]}).encode(), "id1"))
