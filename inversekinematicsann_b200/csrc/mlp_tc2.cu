@@ -43,6 +43,17 @@ constexpr int W_STAGES = 3;
 #ifndef IKB_TS_EPI_WARPS
 #define IKB_TS_EPI_WARPS 16
 #endif
+// Accumulation order within one (layer, N half).  tcgen05.mma truncates the fp32 accumulator toward zero after every
+// K = 16 step, by up to an ulp of the RUNNING SUM.  Interleaved (round 1: per k chunk x_hi w_hi, x_lo w_hi, x_hi w_lo)
+// all 96 steps of an output truncate at the sum's full size.  Corrections first: the 64 steps of the two small
+// products (2^-11 of the result) run while the accumulator is still tiny, and only the 32 steps of x_hi w_hi
+// truncate at full size -- a third of the noise (tools/tc_trunc_model.py replays both orders on the CPU).  The price
+// is that the w_hi tiles pass through shared memory twice (3 tiles per k chunk instead of 2: +50 % L2 -> smem
+// traffic, same MMA count).
+#ifndef IKB_TS_CORR_FIRST
+#define IKB_TS_CORR_FIRST 1
+#endif
+constexpr int TILES_PER_KC = IKB_TS_CORR_FIRST ? 3 : 2;   // weight tiles streamed per k chunk
 constexpr int N_EPI_WARPS = IKB_TS_EPI_WARPS;   // CW warps share the columns of one TMEM sub-partition
 constexpr int CW = N_EPI_WARPS / 4;
 static_assert(CW == 4, "the act_ready granularity (128 features) assumes 4 warps per TMEM sub-partition");
@@ -419,22 +430,27 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_tc2_kernel(const Tc2Args a)
     const long long n_tiles = (a.n + ROWS - 1) / ROWS;
 
     if (warp == 0) {
-        // ===== TMA producer: per layer and N half, for every k chunk the w_hi tile then the w_lo tile =====
+        // ===== TMA producer: the weight tiles of every (layer, N half) in the order the issuer consumes them =====
+        // arena layout: [layer][N half][k chunk][hi | lo] tiles of WTILE_BYTES.
+        // interleaved order: kc0 hi, kc0 lo, kc1 hi, ...; corrections first: (kc hi, kc lo) for all kc, then kc hi again
         if (lane == 0) {
             int s = 0;
             uint32_t ph = 1;
-            const size_t tiles_per_net = (size_t)NM * NHALF * KG * 2;
+            const unsigned char *base = reinterpret_cast<const unsigned char *>(net.w_tiles);
             for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-                const unsigned char *src = reinterpret_cast<const unsigned char *>(net.w_tiles);
-                for (size_t t = 0; t < tiles_per_net; ++t, src += WTILE_BYTES) {
-                    const int nh = (int)((t / (2 * (size_t)KG)) % NHALF);
-                    const uint32_t bytes = (uint32_t)min(256, HP - 256 * nh) * 128u;
-                    mbar_wait(&w_empty[s], ph);
-                    mbar_expect_tx(&w_full[s], bytes);
-                    tma_load_1d(wring + (size_t)s * WTILE_BYTES, src, bytes, &w_full[s]);
-                    if (++s == W_STAGES) {
-                        s = 0;
-                        ph ^= 1;
+                for (int mh = 0; mh < NM * NHALF; ++mh) {
+                    const unsigned char *half_base = base + (size_t)mh * KG * 2 * WTILE_BYTES;
+                    const uint32_t bytes = (uint32_t)min(256, HP - 256 * (mh % NHALF)) * 128u;
+                    for (int t = 0; t < KG * TILES_PER_KC; ++t) {
+                        // t < 2 KG: tile t of the half as stored; after that the hi tile of k chunk t - 2 KG
+                        const int src_tile = t < 2 * KG ? t : 2 * (t - 2 * KG);
+                        mbar_wait(&w_empty[s], ph);
+                        mbar_expect_tx(&w_full[s], bytes);
+                        tma_load_1d(wring + (size_t)s * WTILE_BYTES, half_base + (size_t)src_tile * WTILE_BYTES, bytes, &w_full[s]);
+                        if (++s == W_STAGES) {
+                            s = 0;
+                            ph ^= 1;
+                        }
                     }
                 }
             }
@@ -466,16 +482,24 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_tc2_kernel(const Tc2Args a)
                             }
                             const uint32_t a_cols = a_tmem + kc * 32;  // 64 k = 32 columns of packed fp16 pairs
                             const uint64_t xlo_desc = xlo_desc_base + (uint64_t)(kc * GRAN_DESC);
-                            // w_hi tile: x_hi (TMEM) and x_lo (smem) both multiply it
+                            // w_hi tile
                             { DBG_T0(); mbar_wait(&w_full[s], ph); DBG_ADD(1); }
                             tc_fence_after();
                             uint64_t b_desc = b_desc_base + (uint64_t)(s * WTILE_DESC);
+#if IKB_TS_CORR_FIRST
+                            // corrections first: x_lo (smem) w_hi opens the accumulator, x_hi w_hi waits for the second pass
+#pragma unroll
+                            for (int ks = 0; ks < 4; ++ks)
+                                umma_ss(d_tmem, xlo_desc + 2 * ks, b_desc + 2 * ks, idesc, (kc | ks) != 0);
+#else
+                            // x_hi (TMEM) and x_lo (smem) both multiply it
 #pragma unroll
                             for (int ks = 0; ks < 4; ++ks)
                                 umma_ts(d_tmem, a_cols + ks * 8, b_desc + 2 * ks, idesc, (kc | ks) != 0);
 #pragma unroll
                             for (int ks = 0; ks < 4; ++ks)
                                 umma_ss(d_tmem, xlo_desc + 2 * ks, b_desc + 2 * ks, idesc, 1);
+#endif
                             umma_commit(&w_empty[s]);
                             if (++s == W_STAGES) { s = 0; ph ^= 1; }
                             // w_lo tile: only x_hi multiplies it (x_lo w_lo is below fp32 resolution)
@@ -488,6 +512,20 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_tc2_kernel(const Tc2Args a)
                             umma_commit(&w_empty[s]);
                             if (++s == W_STAGES) { s = 0; ph ^= 1; }
                         }
+#if IKB_TS_CORR_FIRST
+                        // main product last: its 32 steps are the only ones that truncate at the sum's full size
+                        for (int kc = 0; kc < KG; ++kc) {
+                            const uint32_t a_cols = a_tmem + kc * 32;
+                            { DBG_T0(); mbar_wait(&w_full[s], ph); DBG_ADD(1); }
+                            tc_fence_after();
+                            const uint64_t b_desc = b_desc_base + (uint64_t)(s * WTILE_DESC);
+#pragma unroll
+                            for (int ks = 0; ks < 4; ++ks)
+                                umma_ts(d_tmem, a_cols + ks * 8, b_desc + 2 * ks, idesc, 1);
+                            umma_commit(&w_empty[s]);
+                            if (++s == W_STAGES) { s = 0; ph ^= 1; }
+                        }
+#endif
                         umma_commit(d_full);
                     }
                     umma_commit(a_free);  // every read of this layer's x_hi / x_lo has completed
@@ -697,8 +735,9 @@ int ikb_mlp_tc2_pack(IkbMlpTc2 &t, int n_layers, const int *dims, const float *c
             e = 12 - (int)std::ceil(std::log2(wmax));  // largest weight near 2^12: w_lo stays normal, sums stay small
         e = e > 24 ? 24 : (e < -8 ? -8 : e);
         const float sw = std::ldexp(1.0f, e);
-        // three products per K = 16 step share the accumulator (see ikb_tc_truncation_compensation)
-        const int acc_steps = 3 * ((fin + (bias_row >= 0 ? 1 : 0) + 15) / 16);
+        // truncating steps at the sum's full size (see ikb_tc_truncation_compensation): the main product's alone when
+        // the two corrections are accumulated first, all three products' when they are interleaved
+        const int acc_steps = (IKB_TS_CORR_FIRST ? 1 : 3) * ((fin + (bias_row >= 0 ? 1 : 0) + 15) / 16);
         oscale[m] = (float)(ikb_tc_truncation_compensation(acc_steps) / ((double)sw * X_SCALE));
         for (int nhalf = 0; nhalf < NHALF; ++nhalf)
             for (int kc = 0; kc < KG; ++kc) {

@@ -33,6 +33,24 @@ class DenseStack:
             arrays[f'b{i}'] = b
         np.savez(path, **arrays)
 
+    @staticmethod
+    def is_hdf5(path):
+        """True for a real HDF5 file; `<name>.h5` written by save_model without h5py holds the npz container."""
+        with open(path, 'rb') as f:
+            return f.read(8) == b'\x89HDF\r\n\x1a\n'
+
+    def save_h5(self, path):
+        """Keras' legacy HDF5 layout (model_weights/<layer>/<layer>/{kernel:0,bias:0} + layer_names), needs h5py."""
+        import h5py  # optional dependency
+        with h5py.File(path, 'w') as f:
+            group = f.create_group('model_weights')
+            names = [f'dense_{i}' if i else 'dense' for i in range(len(self.kernels))]
+            group.attrs['layer_names'] = [n.encode() for n in names]
+            for name, k, b in zip(names, self.kernels, self.biases):
+                inner = group.create_group(name).create_group(name)
+                inner.create_dataset('kernel:0', data=k)
+                inner.create_dataset('bias:0', data=b)
+
     @classmethod
     def load_npz(cls, path):
         data = np.load(path)
@@ -97,7 +115,9 @@ class ANN:
         from joblib import load
         modelname = model_h5[:-3]
         npz = modelname + '.npz'
-        if os.path.exists(model_h5):
+        if os.path.exists(model_h5) and not DenseStack.is_hdf5(model_h5):
+            self.model = DenseStack.load_npz(model_h5)   # written by save_model() where h5py is absent
+        elif os.path.exists(model_h5):
             try:
                 self.model = DenseStack.load_h5(model_h5)
             except ImportError:
@@ -115,10 +135,16 @@ class ANN:
         return self.model
 
     def save_model(self, prefix='model'):
-        """Save weights as `<prefix>_<timestamp>.npz` and the scalers next to it (ann.py:87-95)."""
+        """Save weights as `<prefix>_<timestamp>.h5` and the scalers next to it (ann.py:87-95).  With h5py the file
+        is HDF5 in Keras' legacy weight layout; without it the same name holds the flat npz container (W0.., b0..),
+        which `load_model` recognises by its magic bytes."""
         from joblib import dump
         stamp = str(datetime.timestamp(datetime.now())).replace('.', '-')
-        self.model.save_npz(f'{prefix}_{stamp}.npz')
+        try:
+            self.model.save_h5(f'{prefix}_{stamp}.h5')
+        except ImportError:
+            with open(f'{prefix}_{stamp}.h5', 'wb') as f:
+                self.model.save_npz(f)
         dump(self.x_data_skaler, f'{prefix}_{stamp}_scaler_x.bin', compress=True)
         dump(self.y_data_skaler, f'{prefix}_{stamp}_scaler_y.bin', compress=True)
         return f'{prefix}_{stamp}'

@@ -6,8 +6,10 @@ signatures and return python lists of [x, y, z] (position_generator.py:26-97).  
 workloads never touch the host.  The random shapes draw from a counter-based Philox stream keyed by
 (seed, row): the same distributions as the reference's ``np.random.rand`` / ``scipy.stats.truncnorm`` calls
 and reproducible per seed, but not numpy's Mersenne-Twister numbers.
-``random`` (position_generator.py:65-70) is not mirrored: upstream it fails on current scikit-learn
-(``minmax_scale`` rejects a list ``feature_range``).
+The shapes upstream only ever builds on the host in small numbers stay host-side NumPy here:
+``random`` (position_generator.py:65-70; upstream it fails on current scikit-learn because ``minmax_scale`` rejects
+a list ``feature_range`` -- the same min-max mapping is done directly), ``distribution='random'`` (:92-95, a shuffled
+linspace) and the python-generator variants ``circle_gen`` / ``cube_random_gen`` (:33-37, 57-63).
 """
 import ctypes
 import math
@@ -77,7 +79,7 @@ class TrainingDataGenerator:
         if distribution == 'uniform':
             lens = [lim[1] - lim[0], lim[3] - lim[2], lim[5] - lim[4]]
             return _generate(GEN_CUBE_RANDOM, lens + [lim[0], lim[2], lim[4]], no_of_samples, seed=seed, **kw)
-        raise ValueError("distribution must be 'normal' or 'uniform' ('random' = shuffled linspace is host-only upstream)")
+        raise ValueError("distribution must be 'normal' or 'uniform' on the device ('random' = shuffled linspace is host-side)")
 
     # ---- reference-shaped forms (python lists) ---------------------------------------------------------
     @staticmethod
@@ -102,8 +104,40 @@ class TrainingDataGenerator:
         return TrainingDataGenerator.spring_device(no_of_samples, len_x, len_y, len_z, dtype="float64").cpu().tolist()
 
     @staticmethod
+    def random(no_of_samples, limits):
+        """Random normal distribution min-max scaled into the limits (position_generator.py:65-70): per axis
+        `minmax_scale(np.random.randn(n), limits[axis])`, i.e. lo + (v - min v) / (max v - min v) * (hi - lo)."""
+        def apply_limits(axis):
+            v = np.random.randn(no_of_samples)
+            lo, hi = limits[axis]
+            span = v.max() - v.min()
+            return lo + (v - v.min()) / (span if span > 0 else 1.0) * (hi - lo)
+        return [[x, y, z] for x, y, z in zip(apply_limits('x'), apply_limits('y'), apply_limits('z'))]
+
+    @staticmethod
+    def circle_gen(radius, no_of_samples, centre):
+        """Circle shape generator, formula as upstream INCLUDING its y term `centre[1] * sin(t)` (no radius, no
+        offset: position_generator.py:33-37 differs from `circle` there)."""
+        for tstamp in range(no_of_samples):
+            yield [centre[0], centre[1] * math.sin(tstamp), centre[2] + radius * math.cos(tstamp)]
+
+    @staticmethod
+    def cube_random_gen(step, len_x, len_y, len_z, start=(0, 0, 0)):
+        """Random cube as a python generator (position_generator.py:57-63): numpy's global stream, x, y, z order."""
+        for _ in np.arange(0, len_x * len_y * len_z, step):
+            yield [len_x * np.random.rand() + start[0], len_y * np.random.rand() + start[1],
+                   len_z * np.random.rand() + start[2]]
+
+    @staticmethod
     def random_distribution(no_of_samples, limits, distribution='normal', std_dev=0.5, seed=1234):
         """Randomly generated data (position_generator.py:80-97)."""
+        if distribution == 'random':   # just randomly shuffled data (:92-95)
+            positions = []
+            for _, limitv in limits.items():
+                arr = np.linspace(limitv[0], limitv[1], no_of_samples)
+                np.random.shuffle(arr)
+                positions.append(arr.tolist())
+            return transpose(positions)
         return TrainingDataGenerator.random_distribution_device(no_of_samples, limits, distribution, std_dev,
                                                                 seed=seed, dtype="float64").cpu().tolist()
 

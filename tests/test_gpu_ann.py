@@ -75,7 +75,7 @@ def test_limits_and_errors(mode):
 
 
 def test_model_files_round_trip(tmp_path):
-    """reference tests/ann_unit.py:23-35 (load_model / save_model), with the flat .npz container."""
+    """reference tests/ann_unit.py:23-35 (load_model / save_model): `<prefix>_<stamp>.h5` + two scaler files."""
     import glob
     from inversekinematicsann_b200.kinematics.ann import ANN
     from inversekinematicsann_b200.robot.robot import SixDOFRobot as R
@@ -86,7 +86,7 @@ def test_model_files_round_trip(tmp_path):
     ann.ann.x_data_skaler, ann.ann.y_data_skaler = sx, sy
     ann.ann._uploaded = False
     prefix = ann.ann.save_model(str(tmp_path / "saved_model"))
-    assert glob.glob(str(tmp_path / "saved_model*.npz"))
+    assert glob.glob(str(tmp_path / "saved_model*.h5"))       # the assertion of tests/ann_unit.py:33
     assert glob.glob(str(tmp_path / "saved_model*_scaler_x.bin")) and glob.glob(str(tmp_path / "saved_model*_scaler_y.bin"))
     fresh = ANN(R.effector_workspace_limits, R.dh_matrix)
     assert fresh.model is None

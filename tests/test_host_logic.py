@@ -129,3 +129,63 @@ def test_raise_from_stats_same_row_in_two_error_classes():
         ik._raise_from_stats([[0, 0, 2]] * 4, IkStats(first_zero_division=3, first_domain_error=3))
     with pytest.raises(ValueError):
         ik._raise_from_stats([[0, 0, 2]] * 4, IkStats(first_zero_division=3, first_domain_error=1))
+
+
+def test_save_model_keeps_the_reference_file_names(tmp_path):
+    """ann.py:87-95: `<prefix>_<stamp>.h5` + `_scaler_x.bin` + `_scaler_y.bin`; load_model finds them again.
+    (No GPU: nothing is predicted.)"""
+    import glob
+    from sklearn.preprocessing import StandardScaler
+    from inversekinematicsann_b200.kinematics.ann import ANN, DenseStack
+    from inversekinematicsann_b200.robot.robot import SixDOFRobot as R
+    rng = np.random.default_rng(0)
+    ann = ANN(R.effector_workspace_limits, R.dh_matrix)
+    ann.model = DenseStack([rng.normal(size=(3, 8)), rng.normal(size=(8, 4))], [rng.normal(size=8), rng.normal(size=4)])
+    ann.x_data_skaler = StandardScaler().fit(rng.normal(size=(50, 3)))
+    ann.y_data_skaler = StandardScaler().fit(rng.normal(size=(50, 4)))
+    prefix = ann.save_model(str(tmp_path / "saved_model"))
+    assert glob.glob(str(tmp_path / "saved_model*.h5")) and glob.glob(str(tmp_path / "saved_model*_scaler_x.bin"))
+    fresh = ANN(R.effector_workspace_limits, R.dh_matrix)
+    assert fresh.load_model(prefix + ".h5") is not None
+    assert fresh.model.layer_dims == [3, 8, 4]
+    np.testing.assert_array_equal(fresh.model.kernels[1], ann.model.kernels[1])
+    np.testing.assert_allclose(fresh.x_data_skaler.mean_, ann.x_data_skaler.mean_)
+
+
+def test_keras_h5_layout_round_trip(tmp_path):
+    """DenseStack.load_h5 on a file in Keras' legacy layout (what tools/h5_to_npz.py converts); needs h5py."""
+    pytest.importorskip("h5py")
+    from inversekinematicsann_b200.kinematics.ann import DenseStack
+    rng = np.random.default_rng(1)
+    stack = DenseStack([rng.normal(size=(3, 16)), rng.normal(size=(16, 16)), rng.normal(size=(16, 4))],
+                       [rng.normal(size=16), rng.normal(size=16), rng.normal(size=4)])
+    path = str(tmp_path / "m.h5")
+    stack.save_h5(path)
+    assert DenseStack.is_hdf5(path)
+    back = DenseStack.load_h5(path)
+    assert back.layer_dims == [3, 16, 16, 4]
+    for a, b in zip(stack.kernels + stack.biases, back.kernels + back.biases):
+        np.testing.assert_array_equal(a, b)
+
+
+def test_host_side_generators_of_the_reference():
+    """position_generator.py:33-37,57-70,92-95: the shapes that stay on the host."""
+    from inversekinematicsann_b200.robot.position_generator import TrainingDataGenerator as G
+    lim = {'x': [0, 3], 'y': [0, 4], 'z': [-1, 5]}
+    np.random.seed(3)
+    pts = np.array(G.random(200, lim))
+    assert pts.shape == (200, 3)
+    for ax, key in enumerate('xyz'):
+        assert pts[:, ax].min() == pytest.approx(lim[key][0]) and pts[:, ax].max() == pytest.approx(lim[key][1])
+    np.random.seed(3)
+    v = np.random.randn(200)
+    np.testing.assert_allclose(pts[:, 0], (v - v.min()) / (v.max() - v.min()) * 3.0, atol=1e-12)
+    shuffled = np.array(G.random_distribution(50, lim, 'random'))
+    assert shuffled.shape == (50, 3)
+    np.testing.assert_allclose(np.sort(shuffled[:, 2]), np.linspace(-1, 5, 50))
+    circ = list(G.circle_gen(2, 5, (1, 3, 2)))
+    assert circ[1] == [1, 3 * np.sin(1), 2 + 2 * np.cos(1)]
+    np.random.seed(4)
+    cloud = list(G.cube_random_gen(1.0, 2, 3, 1, start=(1, 1, 1)))
+    np.random.seed(4)
+    assert len(cloud) == 6 and cloud[0] == [2 * np.random.rand() + 1, 3 * np.random.rand() + 1, np.random.rand() + 1]
