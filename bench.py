@@ -182,7 +182,7 @@ def main():
     from inversekinematicsann_b200.engine import fabrik_algorithmic_flops
     from inversekinematicsann_b200.kinematics.inverse import AnnInverseKinematics, FabrikInverseKinematics
     from inversekinematicsann_b200.robot.robot import SixDOFRobot as R
-    from inversekinematicsann_b200.sharding import reduce_stats
+    from inversekinematicsann_b200.sharding import ShardedFabrik, gather_rows, reduce_stats
 
     def bind_to_gpu_numa_node(index):
         """Pin this rank to the CPUs next to its GPU so that its pinned staging buffers are allocated on the
@@ -247,6 +247,64 @@ def main():
         w1 = time.perf_counter()
         return max_over_ranks(e0.elapsed_time(e1) * 1e-3), w0, w1
 
+    PARITY_ROWS = 100_000
+
+    def reduce_parity(block):
+        """max / p99 -> maximum over ranks, counts -> sums, means -> row-weighted means (every rank checks the first
+        PARITY_ROWS rows of ITS shard against the oracle on its own host cores)."""
+        if world == 1:
+            return block
+        keys = sorted(block)
+        mx = torch.tensor([block[k] for k in keys if k.startswith(("max_", "p99_"))], dtype=torch.float64, device=dev)
+        sm = torch.tensor([block[k] for k in keys if k.startswith(("rows", "n_", "sum_"))], dtype=torch.float64, device=dev)
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        out = dict(block)
+        for k, v in zip([k for k in keys if k.startswith(("max_", "p99_"))], mx.tolist()):
+            out[k] = v
+        for k, v in zip([k for k in keys if k.startswith(("rows", "n_", "sum_"))], sm.tolist()):
+            out[k] = v
+        return out
+
+    def finish_parity(block, tol):
+        """counts / sums -> the fractions and means SURVEY 8d asks for"""
+        rows = max(block["rows"] - block["n_excluded_degenerate"], 1)
+        out = {"rows": int(block["rows"]), "excluded_degenerate": int(block["n_excluded_degenerate"]),
+               "max_abs_dtheta": block["max_abs_dtheta"], "p99": block["p99_abs_dtheta"],
+               f"frac_gt_{tol:g}": block["n_gt_tol"] / rows}
+        if "n_k_mismatch" in block:
+            out["k_mismatch_frac"] = block["n_k_mismatch"] / rows
+        out["fk_err_ref_vs_engine"] = {"reference_mean": block["sum_fk_ref"] / rows, "engine_mean": block["sum_fk_eng"] / rows,
+                                       "max_abs_diff": block["max_fk_diff"]}
+        for k in ("max_abs_dtheta_vs_fp64", "max_abs_dtheta_vs_torch", "max_oracle_fp32_vs_fp64"):
+            if k in block:
+                out[k] = block[k]
+        return out
+
+    def fabrik_parity(xyz_dev, angles_dev, iters_dev, label):
+        """The first PARITY_ROWS rows of THIS launch's inputs and outputs against the CPU oracle
+        (oracle/ik_oracle.c = fabrik.py + inverse.py:54-139 restated): SURVEY 8d 'parity metrics to print'."""
+        from oracle import c_oracle
+        c_oracle.set_num_threads(os.cpu_count() or 1)
+        m = min(PARITY_ROWS, xyz_dev.shape[0])
+        pts = xyz_dev[:m].double().cpu().numpy()             # the float32 inputs, exactly as the kernel read them
+        got = angles_dev[:m].double().cpu().numpy()
+        got_k = iters_dev[:m].cpu().numpy()
+        want = c_oracle.fabrik_ikine(pts)
+        ok = np.isfinite(want["angles"]).all(axis=1) & np.isfinite(got).all(axis=1)
+        d = np.abs(got - want["angles"])[ok].max(axis=1) if ok.any() else np.zeros(1)
+        _, _, fk_ref = c_oracle.fk_positions(want["angles"][ok], targets=pts[ok])
+        _, _, fk_eng = c_oracle.fk_positions(got[ok], targets=pts[ok])
+        block = {"rows": m, "n_excluded_degenerate": int((~ok).sum()), "max_abs_dtheta": float(d.max()),
+                 "p99_abs_dtheta": float(np.quantile(d, 0.99)), "n_gt_tol": int((d > 1e-4).sum()),
+                 "n_k_mismatch": int((got_k[ok] != want["iters"][ok]).sum()),
+                 "sum_fk_ref": float(fk_ref.sum()), "sum_fk_eng": float(fk_eng.sum()),
+                 "max_fk_diff": float(np.abs(fk_ref - fk_eng).max())}
+        out = finish_parity(reduce_parity(block), 1e-4)
+        out["what"] = (f"{label}: rows [0, {m}) of every rank's shard, outputs of the full-size launch (float32 angles) vs "
+                       f"oracle/ik_oracle.c on the same float32 inputs; bar 1e-4 rad, iteration counts exact")
+        return out
+
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
@@ -266,6 +324,7 @@ def main():
     flops_per_launch = fabrik_algorithmic_flops(one.sum_iterations, n)
     launch_s = secs / args.steps
     peak_fp64 = eng.microbench_fma("f64")
+    peak_fp64_theory = eng.theoretical_fma_peak("f64")
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     hbm_peak = json.load(open(peaks_path))["hbm_gbs"] if os.path.exists(peaks_path) else 6650.0
     traffic = None
@@ -280,6 +339,8 @@ def main():
         "frac": flops_per_launch / launch_s / 1e12 / peak_fp64,
         "peak_source": "measured live: DFMA-chain microbenchmark (ikb_microbench_fma); MEASURED_PEAKS.json has no "
                        "CUDA-core figure",
+        "peak_theoretical": peak_fp64_theory, "frac_of_theoretical": flops_per_launch / launch_s / 1e12 / peak_fp64_theory,
+        "peak_theoretical_source": "SMs x 64 fp64 lanes x 2 x max SM clock (cudaDevAttrClockRate)",
         "flops_per_launch": flops_per_launch, "flops_model": "114*sum_iterations + 126*rows (SURVEY 8d)",
         "launch_ms": launch_s * 1e3,
         "hbm": {"achieved": n * 28 / launch_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
@@ -287,6 +348,12 @@ def main():
                 "peak_source": "MEASURED_PEAKS.json" if os.path.exists(peaks_path) else "fallback"},
         "traffic": traffic,
     }
+
+    # parity of THIS launch's rows against the oracle (outside the timed region)
+    it_full = torch.empty(n, device=dev, dtype=torch.int32)
+    eng.fabrik_solve_device(xyz, angles, iters=it_full)
+    parity = {"fabrik_workspace_box": fabrik_parity(xyz, angles, it_full, "cfg 3 (W) cube_random full workspace")}
+    del it_full
 
     # opt-in fp32 iterate (the north star's FP32-pipe variant; outside the parity bar)
     secs32, _, _ = timed_device_loop(lambda: eng.fabrik_solve_device(xyz, angles, precision="f32"), max(2, args.steps // 2), 3)
@@ -337,18 +404,51 @@ def main():
     eng.fabrik_solve_device(xyz_r, ang_r)
     one_r = eng.stats_fetch_torch()
     secs_r, _, _ = timed_device_loop(lambda: eng.fabrik_solve_device(xyz_r, ang_r), args.steps, 3)
+    it_r = torch.empty(xyz_r.shape[0], device=dev, dtype=torch.int32)
+    eng.fabrik_solve_device(xyz_r, ang_r, iters=it_r)
+    parity["fabrik_interior_box"] = fabrik_parity(xyz_r, ang_r, it_r, "cfg 3 (R) cube_random reachable interior")
+    del it_r
     interior = {"value": xyz_r.shape[0] * world * args.steps / secs_r, "unit": UNIT,
                 "rows_per_gpu": xyz_r.shape[0], "mean_iterations": one_r.sum_iterations / xyz_r.shape[0],
                 "fp64_frac": fabrik_algorithmic_flops(one_r.sum_iterations, xyz_r.shape[0]) /
                              (secs_r / args.steps) / 1e12 / peak_fp64}
     del xyz_r, ang_r, err
 
+    # ---- the final result gather (north star: "NCCL is used only for the final result gather") -------
+    gather = None
+    if world > 1:
+        sh = ShardedFabrik(ik)
+        n_total = n * world
+        full = torch.empty(n_total, 4, device=dev, dtype=torch.float32) if rank == 0 else None
+        g_steps = max(2, min(args.steps, 5))
+        only_secs, _, _ = timed_device_loop(lambda: gather_rows(angles, n_total, dst=0, out=full), g_steps, 2)
+        both_secs, _, _ = timed_device_loop(
+            lambda: sh.ikine_device(xyz, angles, n_total=n_total, gather_dst=0, gather_out=full, check=False), g_steps, 2)
+        # every shard must have landed at its own rows of rank 0's buffer
+        probe = torch.zeros(world, dtype=torch.float64, device=dev)
+        probe[rank] = angles[:4096].double().sum() + angles[-4096:].double().sum()
+        dist.all_reduce(probe, op=dist.ReduceOp.SUM)
+        order_ok = None
+        if rank == 0:
+            got = torch.stack([full[r * n: r * n + 4096].double().sum() + full[(r + 1) * n - 4096: (r + 1) * n].double().sum()
+                               for r in range(world)])
+            order_ok = bool(torch.equal(got, probe))
+        moved = (world - 1) * n * 16
+        gather = {"rows_total": n_total, "dst": 0, "bytes_into_dst": moved,
+                  "ms": only_secs / g_steps * 1e3, "GBps_into_dst": moved / (only_secs / g_steps) / 1e9,
+                  "solve_ms": secs / args.steps * 1e3, "overlapped_ms": both_secs / g_steps * 1e3,
+                  "solve_plus_gather_over_solve": (both_secs / g_steps) / (secs / args.steps),
+                  "order_verified": order_ok,
+                  "how": "ShardedFabrik.ikine_device: K1 per 4 Mi-row chunk, finished chunks shipped to rank 0 with NCCL "
+                         "send/recv (point-to-point, received in place) while the next chunk is solved; `ms` is the "
+                         "same gather after the solve, not overlapped"}
+        del full
+
     # ---- FABRIK end to end: host buffers through the public ikine() call --------------------------
+    # page-locked buffers from the library (cudaHostAlloc by this rank after its CPU binding: NUMA-local, not portable)
     m = args.e2e_rows or n
-    host_in = torch.empty(m, 3, dtype=torch.float32, pin_memory=True)
-    host_in.copy_(xyz[:m])
-    host_out = torch.empty(m, 4, dtype=torch.float32, pin_memory=True)
-    h_in, h_out = host_in.numpy(), host_out.numpy()
+    h_in, h_out = eng.pinned_empty((m, 3), np.float32), eng.pinned_empty((m, 4), np.float32)
+    torch.from_numpy(h_in).copy_(xyz[:m])
     del xyz, angles
     e2e_steps = max(2, min(args.steps, 5))
     for _ in range(2):
@@ -359,11 +459,34 @@ def main():
         ik.ikine(h_in, out=h_out)          # H2D + solve + D2H, synchronous at the API boundary
     torch.cuda.synchronize()
     e2e_secs = max_over_ranks(time.perf_counter() - t0)
+    # copy ceiling: the same buffers through the same 3-slot pipeline with the kernels removed, all ranks at once
+    eng.copy_pipeline(h_in, h_out)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        eng.copy_pipeline(h_in, h_out)
+    copy_secs = max_over_ranks(time.perf_counter() - t0)
+    legs = {}
+    for name, src, dst in (("h2d_only", h_in, None), ("d2h_only", None, h_out)):
+        eng.copy_pipeline(src, dst)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            eng.copy_pipeline(src, dst)
+        leg_secs = max_over_ranks(time.perf_counter() - t0)
+        legs[name] = (m * world * e2e_steps * (12 if src is not None else 16)) / leg_secs / 1e9
     e2e = {"value": m * world * e2e_steps / e2e_secs, "unit": UNIT,
            "h2d_bytes_per_step": m * 12 * world, "d2h_bytes_per_step": m * 16 * world,
            "rows_per_gpu": m, "steps": e2e_steps,
-           "api": "FabrikInverseKinematics.ikine(float32 ndarray, out=pinned float32 ndarray)"}
-    del host_in, host_out
+           "api": "FabrikInverseKinematics.ikine(float32 ndarray, out=pinned float32 ndarray)",
+           "copy_ceiling": {"value": m * world * e2e_steps / copy_secs, "unit": UNIT,
+                            "what": "ikb_copy_pipeline_host: the same pinned buffers, chunking and 3 streams per GPU, "
+                                    "kernels removed, all ranks concurrently",
+                            "aggregate_GBps_both_directions": m * world * e2e_steps * 28 / copy_secs / 1e9,
+                            "h2d_alone_GBps": legs["h2d_only"], "d2h_alone_GBps": legs["d2h_only"]},
+           "frac_of_copy_ceiling": copy_secs / e2e_secs,
+           "pinned_memory": "ikb_host_alloc (cudaHostAlloc, default flags) by each rank"}
+    del h_in, h_out
 
     # ---- ANN (config 2) -------------------------------------------------------------------------------
     ann_block = None
@@ -399,15 +522,47 @@ def main():
             a_secs, _, _ = timed_device_loop(lambda: aeng.ann_solve_device(axyz, aout, mode=mode), a_steps, 3)
             gpu_launches += (aeng.launch_count - a_launch0 - 3) * world
             modes[mode] = a_secs / a_steps
-        a_in = torch.empty(an, 3, dtype=torch.float32, pin_memory=True)
-        a_in.copy_(axyz)
-        a_res = torch.empty(an, 4, dtype=torch.float32, pin_memory=True)
-        ann.ikine(a_in.numpy(), out=a_res.numpy())
+        # parity of the default mode's launch on the bench's own rows: NumPy fp32 / fp64 restatements of ann.py:70-76
+        # and an independent torch-CPU fp32 evaluation (oracle/torch_oracle.py); FK error with the oracle's FK
+        aeng.ann_solve_device(axyz, aout, mode="fp16x3_ts")
+        from oracle import c_oracle, np_oracle, torch_oracle
+        from threadpoolctl import threadpool_limits
+        pm = min(PARITY_ROWS, an)
+        p_pts = axyz[:pm].double().cpu().numpy()
+        p_got = aout[:pm].cpu().numpy()
+        sc = (ann.ann.x_data_skaler.mean_, ann.ann.x_data_skaler.scale_, ann.ann.y_data_skaler.mean_,
+              ann.ann.y_data_skaler.scale_)
+        with threadpool_limits(limits=os.cpu_count() or 1):
+            p32 = np_oracle.mlp_predict(p_pts, W, b, *sc, dtype=np.float32)
+            p64 = np_oracle.mlp_predict(p_pts, W, b, *sc, dtype=np.float64)
+        torch.set_num_threads(os.cpu_count() or 1)
+        pt32 = torch_oracle.mlp_predict(p_pts, W, b, *sc)
+        d32 = np.abs(p_got.astype(np.float64) - p32).max(axis=1)
+        _, _, fk_ref = c_oracle.fk_positions(p32.astype(np.float64), targets=p_pts)
+        _, _, fk_eng = c_oracle.fk_positions(p_got.astype(np.float64), targets=p_pts)
+        a_par = finish_parity(reduce_parity({
+            "rows": pm, "n_excluded_degenerate": 0, "max_abs_dtheta": float(d32.max()),
+            "p99_abs_dtheta": float(np.quantile(d32, 0.99)), "n_gt_tol": int((d32 > 1e-5).sum()),
+            "max_abs_dtheta_vs_fp64": float(np.abs(p_got - p64).max()),
+            "max_abs_dtheta_vs_torch": float(np.abs(p_got.astype(np.float64) - pt32).max()),
+            "max_oracle_fp32_vs_fp64": float(np.abs(p32 - p64).max()),
+            "sum_fk_ref": float(fk_ref.sum()), "sum_fk_eng": float(fk_eng.sum()),
+            "max_fk_diff": float(np.abs(fk_ref - fk_eng).max())}), 1e-5)
+        a_par["what"] = (f"cfg 2 random_dist: rows [0, {pm}) of every rank's shard, mlp_tc2_kernel output vs the NumPy fp32 "
+                         f"restatement (max_abs_dtheta, p99, frac), vs its fp64 form and vs torch-CPU fp32 F.linear+tanh; bar "
+                         f"1e-5 rad vs fp32.  Checker weights = this repo's trained network: parity with Keras itself is "
+                         f"UNPINNED (the reference's .h5 is absent from its tree)")
+        parity["ann_random_dist"] = a_par
+        del p32, p64, pt32
+        a_in, a_res = aeng.pinned_empty((an, 3), np.float32), aeng.pinned_empty((an, 4), np.float32)
+        torch.from_numpy(a_in).copy_(axyz)
+        ann.ikine(a_in, out=a_res)
         barrier()
         t0 = time.perf_counter()
         for _ in range(a_steps):
-            ann.ikine(a_in.numpy(), out=a_res.numpy())      # default mode = fp16x3_ts
+            ann.ikine(a_in, out=a_res)      # default mode = fp16x3_ts
         ae2e = max_over_ranks(time.perf_counter() - t0)
+        del a_in, a_res
         peak_fp32 = aeng.microbench_fma("f32")
         tc_s = modes["fp16x3_ts"]
         # FK round trip of the predictions (BASELINE metric: mean FK position error), on the rows FABRIK can reach
@@ -428,6 +583,12 @@ def main():
                   "note": "rows of the workspace sample that FABRIK solves to <= 1e-2 (the population the model was "
                           "trained on); errors come from the ANN kernel's fused FK epilogue"}
         del a_err, f_ang, f_it, f_err
+        ann_traffic = None
+        tpath2 = os.path.join(ROOT, "profiles", "k2_ts_traffic.json")
+        if os.path.exists(tpath2):
+            t2 = json.load(open(tpath2))
+            if t2.get("rows") == an:
+                ann_traffic = t2.get("dram_bytes_per_launch", t2.get("dram_bytes_read", 0) + t2.get("dram_bytes_write", 0))
         # executed tensor-core work: 3 partial products (x_hi w_hi, x_lo w_hi, x_hi w_lo) on the 512-padded layers
         hp = 128 * ((max(aeng.mlp_dims[1:-1]) + 127) // 128)
         executed = 3 * 2.0 * hp * hp * (len(aeng.mlp_dims) - 3) * an
@@ -446,7 +607,7 @@ def main():
                          "flops_per_row": 2 * aeng.mlp_macs_per_row,
                          "executed_tensor_tflops": executed / tc_s / 1e12, "executed_frac": executed / tc_s / 1e12 / bf16_peak,
                          "note": "fp32-grade results need 3 fp16 partial products per algorithmic MAC, so frac <= 1/3 by construction",
-                         "traffic": None},
+                         "traffic": ann_traffic},
             "fp16x3_ss": {"value": an * world / modes["fp16x3"], "unit": UNIT, "kernel": "mlp_tc_kernel",
                           "roofline": {"bound": "tensor", "achieved": flops / modes["fp16x3"] / 1e12, "peak": bf16_peak,
                                        "unit": "TFLOP/s", "frac": flops / modes["fp16x3"] / 1e12 / bf16_peak}},
@@ -527,9 +688,11 @@ def main():
                        "output": "float32 [n,4]", "fabrik_precision": "fp64 iterate + fp64 angle extraction",
                        "mean_iterations": total.sum_iterations / (n * world),
                        "iteration_capped_fraction": total.n_iter_capped / (n * world),
-                       "sharding": f"contiguous ranges, {world} rank(s), no data-path collective",
+                       "sharding": f"contiguous ranges, {world} rank(s), no data-path collective in `value` "
+                                   f"(the final gather to rank 0 is timed separately under \"gather\")",
                        "rank_cpu_affinity": numa_cpus or "unchanged"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(gpu_launches), "roofline": roofline,
+            "parity": parity, "gather": gather,
             "cpu_baseline": cpu_baseline, "fk_error": fk_error, "fabrik_interior_box": interior,
             "fabrik_f32_mode": f32_mode, "ann": ann_block,
             "other_configs": extras,

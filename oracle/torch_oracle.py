@@ -1,0 +1,30 @@
+"""Independent fp32 evaluation of reference kinematics/ann.py:70-76 with torch on the CPU (TEST INFRASTRUCTURE --
+see oracle/__init__.py): a second, third-party implementation of Dense + tanh next to the NumPy restatement in
+np_oracle.mlp_predict, so that the ANN kernels are not only ever compared with the builder's own arithmetic.
+
+``torch.nn.functional.linear`` (oneDNN / MKL GEMM, its own blocking and summation order) and ``torch.tanh`` in
+float32; the scalers follow sklearn's semantics exactly as np_oracle does (transform in float64, cast to float32 for
+the network as Keras does, inverse_transform in place on the float32 prediction).  ANN parity with Keras itself stays
+UNPINNED: neither keras nor the reference's weights exist in this environment.
+"""
+import numpy as np
+
+
+def mlp_predict(xyz, weights, biases, mean_x, scale_x, mean_y, scale_y, chunk=65536):
+    import torch
+    import torch.nn.functional as F
+    xyz = np.asarray(xyz, dtype=np.float64).reshape(-1, 3)
+    Ws = [torch.from_numpy(np.ascontiguousarray(np.asarray(w, dtype=np.float32).T)) for w in weights]   # (out, in)
+    bs = [torch.from_numpy(np.asarray(b, dtype=np.float32)) for b in biases]
+    sy, my = torch.from_numpy(np.asarray(scale_y, np.float32)), torch.from_numpy(np.asarray(mean_y, np.float32))
+    out = np.empty((xyz.shape[0], Ws[-1].shape[0]), dtype=np.float32)
+    with torch.no_grad():
+        for lo in range(0, xyz.shape[0], chunk):
+            xs = (xyz[lo:lo + chunk] - np.asarray(mean_x)) / np.asarray(scale_x)       # StandardScaler.transform, fp64
+            h = torch.from_numpy(xs.astype(np.float32))
+            for W, b in zip(Ws[:-1], bs[:-1]):
+                h = torch.tanh(F.linear(h, W, b))
+            y = F.linear(h, Ws[-1], bs[-1])
+            y.mul_(sy).add_(my)                                                         # inverse_transform, in place
+            out[lo:lo + chunk] = y.numpy()
+    return out
