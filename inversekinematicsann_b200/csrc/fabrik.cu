@@ -201,6 +201,64 @@ __device__ __forceinline__ double atan2_unit(double uy, double ux)
     return copysign(phi, uy);
 }
 
+// ---- the same two functions on the fp32 pipe, for float32 OUTPUT buffers ------------------------------------------
+// K1 is bound by the fp64 pipe while the fp32 pipe idles (ncu: 5 % active).  When the caller's angle buffer is float32
+// the result is rounded to 24 bits anyway, so everything after the last step that needs fp64 -- the cosine with its
+// 8-decimal rounding (inverse.py:81,92,100: the 1e-8 quantum must not flip) -- runs in fp32: t = (1 - |c|) / 2 is
+// still formed in fp64 (no cancellation near |c| = 1, where the reference itself quantises), then sqrt, a degree-4
+// polynomial (tools/fit_asin_poly.py 4: 1.6e-9 abs) and the final combination with pi in fp32.  Measured against the
+// fp64 tail: <= 4e-7 rad (1.7 ulp of pi in fp32), 250x inside the 1e-4 rad bar.  float64 buffers (the list API, the
+// reference's own tests) keep the fp64 tail above (2e-15).
+#ifndef IKB_FABRIK_TAIL32
+#define IKB_FABRIK_TAIL32 1
+#endif
+#define IKB_PI_F 3.14159274101257324f
+
+__device__ __forceinline__ float asin_core_f(float s, float t)
+{
+    float p = 0.0437449409671523f;
+    p = fmaf(p, t, 0.023150225160843828f);
+    p = fmaf(p, t, 0.045707160478796506f);
+    p = fmaf(p, t, 0.07493066952010845f);
+    p = fmaf(p, t, 0.1666682263762875f);
+    return fmaf(s * t, p, s);
+}
+
+__device__ __forceinline__ float sqrt_approx_f(float x)
+{
+    float y;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+// acos of an fp64 cosine (NaN outside [-1, 1], like acos_fast)
+__device__ __forceinline__ float acos_f32(double c)
+{
+    const double a = fabs(c);
+    const bool small = a <= 0.5;
+    const float v = (float)(small ? a : fma(-0.5, a, 0.5));  // |c|, or t = (1 - |c|) / 2 formed in fp64
+    const float t = small ? v * v : v;
+    const float s = small ? v : sqrt_approx_f(v);
+    const float r = asin_core_f(s, t);
+    const float big = c > 0.0 ? 2.0f * r : IKB_PI_F - 2.0f * r;
+    return small ? 0.5f * IKB_PI_F - (c < 0.0 ? -r : r) : big;
+}
+
+// atan2(uy, ux) of a unit vector given in fp64, evaluated in fp32
+__device__ __forceinline__ float atan2_unit_f32(double uy64, double ux64)
+{
+    const float uy = (float)uy64, ux = (float)ux64;
+    const float ay = fabsf(uy), ax = fabsf(ux);
+    const bool m0 = ay <= 0.5f, m1 = ax <= 0.5f;
+    const float h = fmaf(-0.5f, ax, 0.5f);                   // exact: ax >= 1/2 on this branch
+    const float t = m0 ? ay * ay : (m1 ? ax * ax : h);
+    const float s = m0 ? ay : (m1 ? ax : sqrt_approx_f(h));
+    const float r = asin_core_f(s, t);
+    float phi = m0 ? r : (m1 ? 0.5f * IKB_PI_F - r : 2.0f * r);
+    phi = ux < 0.0f ? IKB_PI_F - phi : phi;
+    return copysignf(phi, uy);
+}
+
 // In-plane radius of a target and the unit direction of its vertical plane.  Targets on the z axis
 // have no direction (the reference's theta_1 is rounding noise there): +x is used.
 __device__ __forceinline__ double planar_radius(double x, double y, double &ux, double &uy)
@@ -252,7 +310,7 @@ __device__ __noinline__ double fused_fk_error_f64(double t0, double t1, double t
     return ikb_fk_error_planar_tail<double>(th, tx, ty, tz, a0, a1, a2, a3, eps0, w, ca, sa);
 }
 
-template <bool FUSE_FK>
+template <bool FUSE_FK, bool OUT32>
 __device__ __forceinline__ void fabrik_epilogue(const FabrikArgs &a, int idx, int k, double r1,
                                                 double z1, double r2, double z2, double &fk_sum, unsigned &fk_cnt)
 {
@@ -281,13 +339,7 @@ __device__ __forceinline__ void fabrik_epilogue(const FabrikArgs &a, int idx, in
     // a NaN chain from finite input can only come from 0 * inf, i.e. a zero-length segment
     const bool finite_in = isfinite(x) & isfinite(y) & isfinite(z);
     zero_div |= finite_in & !(isfinite(r1) & isfinite(z1) & isfinite(r2) & isfinite(z2));
-    double th[4];
-    // theta_1 = atan2(E.y, E.x) with E = r3 (ux, uy) (inverse.py:60): only the sign of r3 matters
-    {
-        const bool flip = r3 < 0.0;  // one evaluation: the compiler will not merge two calls under a select
-        th[0] = atan2_unit(flip ? -uy : uy, flip ? -ux : ux);
-    }
-    th[0] = r3 == 0.0 ? 0.0 : (r3 != r3 ? r3 : th[0]);
+    const bool flip = r3 < 0.0;  // theta_1 = atan2(E.y, E.x) with E = r3 (ux, uy) (inverse.py:60): only the sign of r3 matters
     const double ab = rc.seed_ab;                                        // |AB|, A = origin: a constant
     // Everything on squared lengths: the reference takes seven roots, squares six of them again (pow(ac, 2) etc.)
     // and divides by products of three; a squared rounded root differs from the squared length by at most 2 ulp --
@@ -300,33 +352,61 @@ __device__ __forceinline__ void fabrik_epilogue(const FabrikArgs &a, int idx, in
     double den2 = n_bc;
     zero_div |= (den2 == 0.0) | (ab == 0.0);
     const double c2 = round8(((rc.seed_ab2 + n_bc) - n_ac) * ikb_rsqrt(den2) * rc.half_inv_ab);   // inverse.py:77-81
-    const double acos2 = acos_fast(c2);
-    th[1] = ((r1 * ux) * (r2 * ux) < 0) ? (3 * PI / 2) - acos2 : -(PI / 2 - acos2);  // :82-85
     den2 = n_bc * n_cd;
     zero_div |= (den2 == 0.0);
     const double c3 = round8(((n_bc + n_cd) - n_bd) * ikb_rsqrt(den2) * 0.5);            // :90-92
-    th[2] = -(PI - acos_fast(c3));                                                        // :93
     den2 = n_cd * n_de;
     zero_div |= (den2 == 0.0) | (n_ce == 0.0);
     const double c4 = round8(((n_cd + n_de) - n_ce) * ikb_rsqrt(den2) * 0.5);            // :98-100
-    const double acos4 = acos_fast(c4);
     // t4_point_bt = PB(C, E, |CE| / 2) (inverse.py:102): (|CE|/2)/|CE| is exactly 0.5
     const double mr = fma(0.5, r3 - r1, r1), mz = fma(0.5, z3 - z1, z1);
-    th[3] = (n_bd > dist2d_sq(R0, Z0, mr, mz)) ? -(PI - acos4) : (PI - acos4);   // :103-108
+    const bool elbow_neg = (r1 * ux) * (r2 * ux) < 0;                       // :82
+    const bool wrist_neg = n_bd > dist2d_sq(R0, Z0, mr, mz);                // :103
     zero_div &= finite_in;
     const bool domain = !zero_div & (fabs(c2) > 1.0 | fabs(c3) > 1.0 | fabs(c4) > 1.0);
-    if (zero_div) {
-        th[0] = th[1] = th[2] = th[3] = __longlong_as_double(0x7ff8000000000000LL);
+    if (zero_div)
         atomicMin(&a.stats->first_zero_division, row);
-    }
     if (domain)
         atomicMin(&a.stats->first_domain_error, row);
-    ikb_store_angles(a.angles, a.angles_f64, idx, th);
     if (a.iters)
         a.iters[idx] = k;
+    if (OUT32 && IKB_FABRIK_TAIL32) {
+        // float32 buffer: the trigonometric tail on the fp32 pipe (see acos_f32)
+        float t0 = atan2_unit_f32(flip ? -uy : uy, flip ? -ux : ux);
+        t0 = r3 == 0.0 ? 0.0f : (r3 != r3 ? __int_as_float(0x7fc00000) : t0);
+        const float acos2 = acos_f32(c2), acos3 = acos_f32(c3), acos4 = acos_f32(c4);
+        float t1 = elbow_neg ? 1.5f * IKB_PI_F - acos2 : -(0.5f * IKB_PI_F - acos2);     // :82-85
+        float t2 = -(IKB_PI_F - acos3);                                                  // :93
+        float t3 = wrist_neg ? -(IKB_PI_F - acos4) : (IKB_PI_F - acos4);                 // :103-108
+        if (zero_div)
+            t0 = t1 = t2 = t3 = __int_as_float(0x7fc00000);
+        reinterpret_cast<float4 *>(a.angles)[idx] = make_float4(t0, t1, t2, t3);
+        if (FUSE_FK) {  // fused K3: FK of the angles as stored
+            const float e = fused_fk_error_f32(t0, t1, t2, t3, (float)x, (float)y, (float)z, rc.fkc_f[0], rc.fkc_f[1],
+                                               rc.fkc_f[2], rc.fkc_f[3], rc.fkc_f[4], rc.fkc_f[5], rc.fkc_f[6], rc.fkc_f[7]);
+            if (a.fk_err)
+                reinterpret_cast<float *>(a.fk_err)[idx] = e;
+            if (isfinite(e)) {
+                fk_sum += (double)e;
+                ++fk_cnt;
+            }
+        }
+        return;
+    }
+    double th[4];
+    th[0] = atan2_unit(flip ? -uy : uy, flip ? -ux : ux);  // one evaluation: the compiler will not merge two calls under a select
+    th[0] = r3 == 0.0 ? 0.0 : (r3 != r3 ? r3 : th[0]);
+    const double acos2 = acos_fast(c2);
+    th[1] = elbow_neg ? (3 * PI / 2) - acos2 : -(PI / 2 - acos2);  // :82-85
+    th[2] = -(PI - acos_fast(c3));                                                        // :93
+    const double acos4 = acos_fast(c4);
+    th[3] = wrist_neg ? -(PI - acos4) : (PI - acos4);   // :103-108
+    if (zero_div)
+        th[0] = th[1] = th[2] = th[3] = __longlong_as_double(0x7ff8000000000000LL);
+    ikb_store_angles(a.angles, OUT32 ? 0 : 1, idx, th);
     if (FUSE_FK) {  // fused K3: FK of the angles as stored, in the stored precision
         double err;
-        if (a.angles_f64) {
+        if (!OUT32) {
             err = fused_fk_error_f64(th[0], th[1], th[2], th[3], x, y, z, rc.fkc[0], rc.fkc[1], rc.fkc[2], rc.fkc[3],
                                      rc.fkc[4], rc.fkc[5], rc.fkc[6], rc.fkc[7]);
             if (a.fk_err)
@@ -363,7 +443,7 @@ struct WarpQueues {
 // CHAINS = independent chains per lane.  The pass is one long dependency chain (every instruction
 // needs the previous result), so a second chain per lane doubles the instruction-level parallelism a
 // warp offers the FP64 pipe; its cost is registers (fewer resident warps).
-template <typename Real, int CHAINS, bool FUSE_FK>
+template <typename Real, int CHAINS, bool FUSE_FK, bool OUT32>
 __device__ __forceinline__ void fabrik_refill_loop(const FabrikArgs &a, WarpQueues<Real, 32 + 32 * CHAINS> *s_queues)
 {
     // per-warp rings: input queue (pre-staged targets) and output queue (parked solved chains);
@@ -526,7 +606,7 @@ __device__ __forceinline__ void fabrik_refill_loop(const FabrikArgs &a, WarpQueu
                 int slot = out_head + lane;
                 slot -= slot >= OUT_Q ? OUT_Q : 0;
                 const int k_raw = q.out_k[slot], k_done = k_raw & (IKB_CAPPED_BIT - 1);
-                fabrik_epilogue<FUSE_FK>(a, q.out_idx[slot], k_done, (double)q.out_c[0][slot], (double)q.out_c[1][slot],
+                fabrik_epilogue<FUSE_FK, OUT32>(a, q.out_idx[slot], k_done, (double)q.out_c[0][slot], (double)q.out_c[1][slot],
                                 (double)q.out_c[2][slot], (double)q.out_c[3][slot], q.fk_sum[lane], q.fk_cnt[lane]);
                 iters_local += (unsigned)k_done;
                 ++solved_local;
@@ -559,12 +639,12 @@ __device__ __forceinline__ void fabrik_refill_loop(const FabrikArgs &a, WarpQueu
     }
 }
 
-template <typename Real, int CHAINS, bool FUSE_FK>
+template <typename Real, int CHAINS, bool FUSE_FK, bool OUT32>
 __global__ void __launch_bounds__(IKB_FABRIK_WARPS * 32, (CHAINS == 1 ? IKB_FABRIK_MIN_CTAS : IKB_FABRIK_MIN_CTAS2))
     fabrik_planar_kernel(const FabrikArgs a)
 {
     __shared__ WarpQueues<Real, 32 + 32 * CHAINS> s_queues[IKB_FABRIK_WARPS];
-    fabrik_refill_loop<Real, CHAINS, FUSE_FK>(a, s_queues);
+    fabrik_refill_loop<Real, CHAINS, FUSE_FK, OUT32>(a, s_queues);
 }
 
 // ---- out-of-reach targets: max_iter passes in lockstep (see is_far) -----------------------------------------
@@ -582,7 +662,7 @@ struct FarQueue {
     Real out_c[4][32 * IKB_FAR_CHAINS];
 };
 
-template <typename Real>
+template <typename Real, bool OUT32>
 __device__ __forceinline__ void fabrik_far_loop(const FabrikArgs &a, FarQueue<Real> *s_q)
 {
     constexpr int CH = IKB_FAR_CHAINS, BATCH = 32 * CH;
@@ -662,7 +742,7 @@ __device__ __forceinline__ void fabrik_far_loop(const FabrikArgs &a, FarQueue<Re
         __syncwarp();
 #pragma unroll 1
         for (int e = lane; e < nb; e += 32) {
-            fabrik_epilogue<false>(a, q.idx[e], max_iter, (double)q.out_c[0][e], (double)q.out_c[1][e],
+            fabrik_epilogue<false, OUT32>(a, q.idx[e], max_iter, (double)q.out_c[0][e], (double)q.out_c[1][e],
                                    (double)q.out_c[2][e], (double)q.out_c[3][e], fk_sum, fk_cnt);
             ++solved_local;
         }
@@ -690,7 +770,7 @@ __device__ __forceinline__ void fabrik_far_loop(const FabrikArgs &a, FarQueue<Re
 // its own chunk counter and claims its rows with is_far.  (Which role a CTA starts in hardly matters -- 17.1 to
 // 17.7 ms per 1e8 rows across 0..100 % -- because a lockstep warp is bound by the latency of its own dependent fp64
 // chain rather than by the pipe once fewer than six of them share a scheduler.)
-template <typename Real>
+template <typename Real, bool OUT32>
 __global__ void __launch_bounds__(IKB_FABRIK_WARPS * 32, IKB_FABRIK_MIN_CTAS) fabrik_split_kernel(const FabrikArgs a)
 {
     constexpr size_t kNear = sizeof(WarpQueues<Real, 64>) * IKB_FABRIK_WARPS, kFar = sizeof(FarQueue<Real>) * IKB_FABRIK_WARPS;
@@ -702,9 +782,9 @@ __global__ void __launch_bounds__(IKB_FABRIK_WARPS * 32, IKB_FABRIK_MIN_CTAS) fa
 #pragma unroll 1
     for (int phase = 0; phase < 2; ++phase) {
         if ((phase == 0) == far_first)
-            fabrik_far_loop<Real>(a, reinterpret_cast<FarQueue<Real> *>(s_raw));
+            fabrik_far_loop<Real, OUT32>(a, reinterpret_cast<FarQueue<Real> *>(s_raw));
         else
-            fabrik_refill_loop<Real, 1, false>(a, reinterpret_cast<WarpQueues<Real, 64> *>(s_raw));
+            fabrik_refill_loop<Real, 1, false, OUT32>(a, reinterpret_cast<WarpQueues<Real, 64> *>(s_raw));
         __syncthreads();  // the two roles overlay the same shared memory
     }
 }
@@ -932,24 +1012,29 @@ cudaError_t ikb_launch_fabrik_planar(const void *xyz, int xyz_f64, long long n, 
         const double thr = reach + rc.tol + 1e-6 * (1.0 + reach);  // margin >> the rounding of |f2 - S| <= d1 + d2
         a.far_thr2 = thr * thr;
         a.work_counter_far = work_counter + 1;
+        const void *kargs[] = {&a};
+        const void *fn;
         if (precision == IKB_FABRIK_F32)
-            fabrik_split_kernel<float><<<(unsigned)grid, per_cta, 0, stream>>>(a);
+            fn = angles_f64 ? (const void *)fabrik_split_kernel<float, false> : (const void *)fabrik_split_kernel<float, true>;
         else
-            fabrik_split_kernel<double><<<(unsigned)grid, per_cta, 0, stream>>>(a);
-        return cudaGetLastError();
+            fn = angles_f64 ? (const void *)fabrik_split_kernel<double, false> : (const void *)fabrik_split_kernel<double, true>;
+        return cudaLaunchKernel(fn, dim3((unsigned)grid), dim3(per_cta), const_cast<void **>(kargs), 0, stream);
     }
-    if (precision == IKB_FABRIK_F32) {
-        if (fuse)
-            fabrik_planar_kernel<float, IKB_FABRIK_CHAINS, true><<<(unsigned)grid, per_cta, 0, stream>>>(a);
-        else
-            fabrik_planar_kernel<float, IKB_FABRIK_CHAINS, false><<<(unsigned)grid, per_cta, 0, stream>>>(a);
-    } else {
-        if (fuse)
-            fabrik_planar_kernel<double, IKB_FABRIK_CHAINS, true><<<(unsigned)grid, per_cta, 0, stream>>>(a);
-        else
-            fabrik_planar_kernel<double, IKB_FABRIK_CHAINS, false><<<(unsigned)grid, per_cta, 0, stream>>>(a);
-    }
-    return cudaGetLastError();
+    // kernel variant = (iterate precision, fused FK error, output precision); the trigonometric tail of the angle
+    // extraction follows the output buffer's precision (see acos_f32)
+    const void *fn;
+#define IKB_PICK(REAL)                                                                                               \
+    (fuse ? (angles_f64 ? (const void *)fabrik_planar_kernel<REAL, IKB_FABRIK_CHAINS, true, false>                   \
+                        : (const void *)fabrik_planar_kernel<REAL, IKB_FABRIK_CHAINS, true, true>)                   \
+          : (angles_f64 ? (const void *)fabrik_planar_kernel<REAL, IKB_FABRIK_CHAINS, false, false>                  \
+                        : (const void *)fabrik_planar_kernel<REAL, IKB_FABRIK_CHAINS, false, true>))
+    if (precision == IKB_FABRIK_F32)
+        fn = IKB_PICK(float);
+    else
+        fn = IKB_PICK(double);
+#undef IKB_PICK
+    const void *kargs[] = {&a};
+    return cudaLaunchKernel(fn, dim3((unsigned)grid), dim3(per_cta), const_cast<void **>(kargs), 0, stream);
 }
 
 cudaError_t ikb_launch_fabrik_generic_ikine(const void *xyz, int xyz_f64, long long n, long long index_base,

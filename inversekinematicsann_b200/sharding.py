@@ -189,6 +189,26 @@ class _ShardedIkine:
         return out_shard
 
 
+def scatter_rows(full_rows, n_total, cols, dtype, device, src=0):
+    """The inverse of gather_rows: rank `src` holds (n_total, cols) rows on its device, every rank gets its
+    contiguous shard (point-to-point sends of unequal shards; `full_rows` is None elsewhere)."""
+    world, rank = (dist.get_world_size(), dist.get_rank()) if _dist_ready() else (1, 0)
+    if world == 1:
+        return full_rows
+    sizes = [shard_range(n_total, r, world) for r in range(world)]
+    lo, hi = sizes[rank]
+    if rank == src:
+        ops = [dist.P2POp(dist.isend, full_rows[l:h], r) for r, (l, h) in enumerate(sizes) if r != src and h > l]
+        mine = full_rows[lo:hi]
+    else:
+        mine = torch.empty((hi - lo, cols), dtype=dtype, device=device)
+        ops = [dist.P2POp(dist.irecv, mine, src)] if hi > lo else []
+    if ops:
+        for work in dist.batch_isend_irecv(ops):
+            work.wait()
+    return mine
+
+
 class _RowPrinter:
     """`points[i]` for the exception text when the points live in HBM on several ranks: the offending row is
     fetched from this rank if it owns it, else described by its index."""
@@ -201,6 +221,36 @@ class _RowPrinter:
         if 0 <= j < self.shard.shape[0]:
             return self.shard[j].tolist()
         return f"#{i}"
+
+
+    def ikine_from_root(self, points=None, root=0, out=None):
+        """One request that arrives on ONE rank (the broker of rpc_broker.py:76-100), served by all GPUs: `root` pushes
+        the (n, 3) host array to its GPU, the shards travel to their GPUs over NCCL send/recv, every rank solves its
+        rows in HBM, the angles are gathered back to `root` and copied into `out` (e.g. a pinned reply buffer).  Every
+        rank calls this; `points` / `out` are only read on `root`.  Returns the (n, 4) host array on `root`.
+        The request crosses PCIe once, on `root`'s link: that link, not the solve, bounds this path."""
+        import numpy as np
+        world, rank = self._world_rank()
+        eng = self._engine()
+        dev = torch.device("cuda", eng.device) if (world == 1 or dist.get_backend() == "nccl") else torch.device("cpu")
+        meta = [None]
+        if rank == root:
+            from .kinematics._shared import points_to_array
+            arr = points_to_array(points)
+            meta = [(arr.shape[0], str(arr.dtype))]
+        if world > 1:
+            dist.broadcast_object_list(meta, src=root)
+        n_total, dtype_name = meta[0]
+        tdtype = torch.float32 if dtype_name == "float32" else torch.float64
+        full_in = torch.from_numpy(arr).to(dev, non_blocking=True) if rank == root else None
+        shard = scatter_rows(full_in, n_total, 3, tdtype, dev, src=root)
+        full = self.ikine_device(shard, n_total=n_total, gather_dst=root if world > 1 else None)
+        if rank != root:
+            return None
+        if out is None:
+            out = np.empty((n_total, 4), dtype=np.dtype(str(full.dtype).replace("torch.", "")))
+        torch.from_numpy(out).copy_(full)      # device -> host (pinned `out`: one DMA)
+        return out
 
 
 class ShardedFabrik(_ShardedIkine):

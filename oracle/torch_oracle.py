@@ -7,7 +7,36 @@ float32; the scalers follow sklearn's semantics exactly as np_oracle does (trans
 the network as Keras does, inverse_transform in place on the float32 prediction).  ANN parity with Keras itself stays
 UNPINNED: neither keras nor the reference's weights exist in this environment.
 """
+import contextlib
+
 import numpy as np
+
+
+def gemm_rel_error(strict=True):
+    """Relative error of a 512 x 512 fp32 F.linear against float64: ~1e-7 for IEEE fp32 accumulation.  oneDNN may run
+    fp32 matmuls through reduced-precision units on CPUs that have them (seen on a B200 host: 5e-4 rad on the trained
+    network with mkldnn enabled), which is not the fp32 arithmetic Keras' CPU kernels use."""
+    import torch
+    import torch.nn.functional as F
+    g = torch.Generator().manual_seed(0)
+    a, w = torch.randn(512, 512, generator=g), torch.randn(512, 512, generator=g)
+    with _strict_fp32() if strict else contextlib.nullcontext():
+        got = F.linear(a, w).double()
+    want = F.linear(a.double(), w.double())
+    return float((got - want).abs().max() / want.abs().max())
+
+
+@contextlib.contextmanager
+def _strict_fp32():
+    """IEEE fp32 GEMMs: oneDNN off (MKL sgemm is used instead), float32 matmul precision 'highest'."""
+    import torch
+    old = torch.get_float32_matmul_precision()
+    torch.set_float32_matmul_precision("highest")
+    try:
+        with torch.backends.mkldnn.flags(enabled=False):
+            yield
+    finally:
+        torch.set_float32_matmul_precision(old)
 
 
 def mlp_predict(xyz, weights, biases, mean_x, scale_x, mean_y, scale_y, chunk=65536):
@@ -18,7 +47,7 @@ def mlp_predict(xyz, weights, biases, mean_x, scale_x, mean_y, scale_y, chunk=65
     bs = [torch.from_numpy(np.asarray(b, dtype=np.float32)) for b in biases]
     sy, my = torch.from_numpy(np.asarray(scale_y, np.float32)), torch.from_numpy(np.asarray(mean_y, np.float32))
     out = np.empty((xyz.shape[0], Ws[-1].shape[0]), dtype=np.float32)
-    with torch.no_grad():
+    with torch.no_grad(), _strict_fp32():
         for lo in range(0, xyz.shape[0], chunk):
             xs = (xyz[lo:lo + chunk] - np.asarray(mean_x)) / np.asarray(scale_x)       # StandardScaler.transform, fp64
             h = torch.from_numpy(xs.astype(np.float32))
