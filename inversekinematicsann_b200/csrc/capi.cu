@@ -307,6 +307,10 @@ int ikb_engine_create(const ikb_config *cfg, ikb_engine **out)
         rc.seed_ab = std::sqrt(rc.seed_r[0] * rc.seed_r[0] + rc.seed_z[0] * rc.seed_z[0]);
         rc.seed_ab2 = rc.seed_ab * rc.seed_ab;
         rc.half_inv_ab = 0.5 / rc.seed_ab;
+        const double d1 = cfg->links[1], d2 = cfg->links[2], d3 = cfg->links[3];
+        rc.cos_sum[0] = rc.seed_ab2 + d1 * d1; rc.cos_inv[0] = 1.0 / (2.0 * rc.seed_ab * d1);
+        rc.cos_sum[1] = d1 * d1 + d2 * d2;     rc.cos_inv[1] = 1.0 / (2.0 * d1 * d2);
+        rc.cos_sum[2] = d2 * d2 + d3 * d3;     rc.cos_inv[2] = 1.0 / (2.0 * d2 * d3);
     }
     *out = e;
     return IKB_OK;

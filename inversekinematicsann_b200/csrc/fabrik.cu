@@ -10,12 +10,18 @@
 //  * P0 is pinned to the start joint and P3 is only needed at the end, so one iteration is
 //    4 point-at-distance updates + 5 reciprocal square roots; the two convergence errors are
 //    | |S - b1| - d0 | and | |T - f2| - d3 | (algebraically the reference's |b0 - S|, |f3 - T|).
-//  * Iteration counts are bimodal (3..8 inside the workspace, exactly max_iter outside), so lanes
-//    are REFILLED: a lane that converges parks its chain in a per-warp shared-memory queue and
-//    takes the next target from a pre-staged input queue; the expensive fp64 epilogue (8 sqrt,
-//    3 acos, atan2) runs only when 32 parked chains are available, i.e. always at full warp width.
-//  * Work is handed out in chunks of IKB_FABRIK_CHUNK consecutive targets from a global counter
-//    (persistent warps, no tail imbalance); row i of the output always belongs to row i of the input.
+//  * ONE scan of the input: persistent warps pull chunks of IKB_FABRIK_CHUNK consecutive targets from a global
+//    counter, classify every target when it is staged (workspace limits, in-plane radius, theta_1 of its plane,
+//    reachable / out of reach) and queue it in shared memory; the rows of the next staging step are loaded before
+//    the pass loop and consumed after it.
+//  * Iteration counts are bimodal (3..8 inside the workspace, exactly max_iter outside).  Reachable targets run with
+//    LANE REFILL: a lane that converges parks its chain (with everything the angle extraction needs about its
+//    target) in a per-warp ring and takes the next staged target in the same step, so the pass loop stays at full
+//    width.  Out-of-reach targets run in LOCKSTEP batches of 64, two chains per lane, exactly max_iter passes with
+//    no verdict, vote or parking, while the warp's reachable chains wait in registers.
+//  * The angle extraction runs on 32 parked chains at once; its cosines and their 8-decimal rounding are fp64,
+//    the trigonometric tail follows the precision of the caller's angle buffer (fp32 pipe for float32 buffers).
+//  * Row i of the output always belongs to row i of the input, whatever order lanes finish in.
 #include <cstdlib>
 
 #include "fk_device.cuh"
@@ -25,12 +31,6 @@
 #define IKB_Q 64  // per-warp input queue capacity (ring), power of two
 #ifndef IKB_FABRIK_MIN_CTAS
 #define IKB_FABRIK_MIN_CTAS 3
-#endif
-#ifndef IKB_FABRIK_MIN_CTAS2
-#define IKB_FABRIK_MIN_CTAS2 2
-#endif
-#ifndef IKB_FABRIK_CHAINS
-#define IKB_FABRIK_CHAINS 1
 #endif
 
 namespace {
@@ -47,8 +47,7 @@ struct FabrikArgs {
     int fk_stats;  // accumulate sum_fk_error / n_fk_error even without the per-row array
     IkbDeviceStats *stats;
     unsigned long long *work_counter;
-    unsigned long long *work_counter_far;
-    double far_thr2;  // > 0: targets with |T - S|^2 above it belong to fabrik_far_kernel (see is_far)
+    double far_thr2;  // > 0: targets with |T - S|^2 above it run in lockstep batches (see is_far)
     IkbRobot rc;
 };
 
@@ -127,9 +126,20 @@ __device__ __forceinline__ bool fabrik_pass(PlanarChain<Real> &c, Real Tr, Real 
     return start_off | goal_band.outside(n2);                            // fabrik.py:63
 }
 
-#ifndef IKB_FABRIK_IDLE_T
-#define IKB_FABRIK_IDLE_T 8  // lanes allowed to sit idle before the warp leaves its inner loop to refill
+#ifndef IKB_FABRIK_LOW_WATER
+#define IKB_FABRIK_LOW_WATER 8  // staged targets below which the warp leaves its pass loop to stage more (while input is left)
 #endif
+
+// theta_1 of a target's plane is evaluated when the target is staged and travels with the chain in the precision of
+// the output buffer
+template <bool OUT32>
+struct TailType {
+    using type = double;
+};
+template <>
+struct TailType<true> {
+    using type = float;
+};
 
 // sqrt(x) for x >= 0 through the reciprocal square root (2 ulp); exact 0 for x == 0
 __device__ __forceinline__ double fast_sqrt(double x)
@@ -310,69 +320,96 @@ __device__ __noinline__ double fused_fk_error_f64(double t0, double t1, double t
     return ikb_fk_error_planar_tail<double>(th, tx, ty, tz, a0, a1, a2, a3, eps0, w, ca, sa);
 }
 
-template <bool FUSE_FK, bool OUT32>
-__device__ __forceinline__ void fabrik_epilogue(const FabrikArgs &a, int idx, int k, double r1,
-                                                double z1, double r2, double z2, double &fk_sum, unsigned &fk_cnt)
+// Bits riding in a chain's iteration counter (the count itself is below 2^28).
+#define IKB_K_MASK 0x0fffffff
+#define IKB_CAPPED_BIT 0x40000000  // the chain stopped on max_iter, not on the tolerance
+#define IKB_UXZERO_BIT 0x20000000  // the target's x is exactly 0: C.x * D.x of inverse.py:82 is 0, never negative
+
+// Finish one solved chain: derive the effector, extract the four angles as reference inverse.py:54-112 does, write
+// the outputs, raise the per-row flags.  Everything it needs about the target travels with the parked chain (Tr, Tz,
+// theta_1 of the target's plane, the x == 0 flag): no second read of the input (round 1 re-read the row here).
+// CONST_LINKS: the chain was iterated in fp64, so its segments have their link lengths to the last place (see below);
+// an fp32-iterated chain is only good to 1e-7 there and takes the general form with computed lengths.
+template <bool FUSE_FK, bool OUT32, bool CONST_LINKS, typename Th1>
+__device__ __forceinline__ void fabrik_epilogue(const FabrikArgs &a, int idx, int k_raw, double r1, double z1, double r2,
+                                                double z2, double Tr, double Tz, Th1 th1, double &fk_sum, unsigned &fk_cnt)
 {
     const IkbRobot &rc = a.rc;
     const double PI = 3.141592653589793;
-    double x, y, z;
-    ikb_load_xyz(a.xyz, a.xyz_f64, idx, x, y, z);
+    const int k = k_raw & IKB_K_MASK;
     const long long row = a.index_base + idx;
-    if (ikb_out_of_limits(rc, x, y, z))
-        atomicMin(&a.stats->first_out_of_limits, row);
-    double ux, uy;
-    const double Tr = planar_radius(x, y, ux, uy), Tz = z;
     const double R0 = rc.seed_r[0], Z0 = rc.seed_z[0];
-    double r3, z3;
-    bool zero_div = false;
-    if (k == 0) {  // the reference's loop never ran: the chain is the seed chain
-        r1 = rc.seed_r[1]; z1 = rc.seed_z[1]; r2 = rc.seed_r[2]; z2 = rc.seed_z[2];
-        r3 = rc.seed_r[3]; z3 = rc.seed_z[3];
-    } else {       // f3 = PB(f2, T, d3) (fabrik.py:40)
+    double r3, z3, c2, c3, c4, n_bd, n_ce;
+    bool odd;  // anything that needs the slow classification below: a cosine outside [-1, 1], NaN, a zero length
+    double n2 = 1.0;
+    if (!rc.zero_iter) {  // f3 = PB(f2, T, d3) (fabrik.py:40)
         const double dr = Tr - r2, dz = Tz - z2;
-        const double n2 = fma(dz, dz, dr * dr);
-        zero_div |= (n2 == 0.0);
+        n2 = fma(dz, dz, dr * dr);
         const double s = ikb_rsqrt_times(n2, rc.link_k[3]);
         r3 = fma(s, dr, r2); z3 = fma(s, dz, z2);
+    } else {  // the reference's loop never ran (tol >= 1 or max_iter <= 0): the chain is the seed chain
+        r1 = rc.seed_r[1]; z1 = rc.seed_z[1]; r2 = rc.seed_r[2]; z2 = rc.seed_z[2];
+        r3 = rc.seed_r[3]; z3 = rc.seed_z[3];
     }
-    // a NaN chain from finite input can only come from 0 * inf, i.e. a zero-length segment
-    const bool finite_in = isfinite(x) & isfinite(y) & isfinite(z);
-    zero_div |= finite_in & !(isfinite(r1) & isfinite(z1) & isfinite(r2) & isfinite(z2));
+    if (CONST_LINKS && !rc.zero_iter) {
+        // The three cosines of inverse.py:77-100 on squared lengths.  After at least one pass B = S and C, D, E are
+        // points at distance d1, d2, d3 from their predecessor (f1 = PB(S, b1, d1) etc.), so |BC|, |CD|, |DE| ARE the
+        // link lengths up to the last-place rounding the reference's own sqrt / division carry -- the same order as
+        // replacing a squared rounded root by the squared length, which this epilogue does throughout.  That leaves
+        // three computed squared lengths (|AC|, |BD|, |CE|) and makes every denominator a constant of the arm:
+        //   cos = (l1^2 + l2^2 - opposite^2) / (2 l1 l2)  ->  (sum_k - opposite^2) * inv_k   (host constants)
+        const double n_ac = fma(z1, z1, r1 * r1);
+        n_bd = dist2d_sq(R0, Z0, r2, z2);
+        n_ce = dist2d_sq(r1, z1, r3, z3);
+        c2 = round8((rc.cos_sum[0] - n_ac) * rc.cos_inv[0]);   // inverse.py:77-81
+        c3 = round8((rc.cos_sum[1] - n_bd) * rc.cos_inv[1]);   // :90-92
+        c4 = round8((rc.cos_sum[2] - n_ce) * rc.cos_inv[2]);   // :98-100
+        // |c| <= 1 is false for NaN as well: a chain that went NaN / inf through 0 * inf inside a pass ends up here
+        odd = !((fabs(c2) <= 1.0) & (fabs(c3) <= 1.0) & (fabs(c4) <= 1.0)) | (n2 == 0.0) | (n_ce == 0.0);
+    } else {
+        // the general form with computed segment lengths: the seed chain (its segments are whatever the DH table
+        // says) and fp32-iterated chains
+        const double n_bc = dist2d_sq(R0, Z0, r1, z1), n_cd = dist2d_sq(r1, z1, r2, z2), n_de = dist2d_sq(r2, z2, r3, z3);
+        const double n_ac = fma(z1, z1, r1 * r1);
+        n_bd = dist2d_sq(R0, Z0, r2, z2);
+        n_ce = dist2d_sq(r1, z1, r3, z3);
+        const double den3 = n_bc * n_cd, den4 = n_cd * n_de;
+        c2 = round8(((rc.seed_ab2 + n_bc) - n_ac) * ikb_rsqrt(n_bc) * rc.half_inv_ab);
+        c3 = round8(((n_bc + n_cd) - n_bd) * ikb_rsqrt(den3) * 0.5);
+        c4 = round8(((n_cd + n_de) - n_ce) * ikb_rsqrt(den4) * 0.5);
+        odd = !((fabs(c2) <= 1.0) & (fabs(c3) <= 1.0) & (fabs(c4) <= 1.0)) | (den3 == 0.0) | (den4 == 0.0) | (n_ce == 0.0) |
+              (n2 == 0.0);
+    }
     const bool flip = r3 < 0.0;  // theta_1 = atan2(E.y, E.x) with E = r3 (ux, uy) (inverse.py:60): only the sign of r3 matters
-    const double ab = rc.seed_ab;                                        // |AB|, A = origin: a constant
-    // Everything on squared lengths: the reference takes seven roots, squares six of them again (pow(ac, 2) etc.)
-    // and divides by products of three; a squared rounded root differs from the squared length by at most 2 ulp --
-    // the order of this epilogue's own rounding -- so no root is taken except inside the three cosines' rsqrt, and the
-    // "bd > dista" test of inverse.py:103 compares squares.
-    const double n_bc = dist2d_sq(R0, Z0, r1, z1), n_cd = dist2d_sq(r1, z1, r2, z2), n_de = dist2d_sq(r2, z2, r3, z3);
-    const double n_ac = fma(z1, z1, r1 * r1), n_bd = dist2d_sq(R0, Z0, r2, z2), n_ce = dist2d_sq(r1, z1, r3, z3);
-    // cos = numerator / (2 |.| |.|) = numerator * rsqrt(product of the squared lengths) / 2: one reciprocal square
-    // root per angle instead of two roots and a division (|AB| is a constant of the arm)
-    double den2 = n_bc;
-    zero_div |= (den2 == 0.0) | (ab == 0.0);
-    const double c2 = round8(((rc.seed_ab2 + n_bc) - n_ac) * ikb_rsqrt(den2) * rc.half_inv_ab);   // inverse.py:77-81
-    den2 = n_bc * n_cd;
-    zero_div |= (den2 == 0.0);
-    const double c3 = round8(((n_bc + n_cd) - n_bd) * ikb_rsqrt(den2) * 0.5);            // :90-92
-    den2 = n_cd * n_de;
-    zero_div |= (den2 == 0.0) | (n_ce == 0.0);
-    const double c4 = round8(((n_cd + n_de) - n_ce) * ikb_rsqrt(den2) * 0.5);            // :98-100
     // t4_point_bt = PB(C, E, |CE| / 2) (inverse.py:102): (|CE|/2)/|CE| is exactly 0.5
     const double mr = fma(0.5, r3 - r1, r1), mz = fma(0.5, z3 - z1, z1);
-    const bool elbow_neg = (r1 * ux) * (r2 * ux) < 0;                       // :82
+    // C.x * D.x < 0 (:82) with C.x = r1 ux, D.x = r2 ux: the sign of r1 r2 unless the plane has no x component
+    const bool elbow_neg = !(k_raw & IKB_UXZERO_BIT) & (r1 * r2 < 0);
     const bool wrist_neg = n_bd > dist2d_sq(R0, Z0, mr, mz);                // :103
-    zero_div &= finite_in;
-    const bool domain = !zero_div & (fabs(c2) > 1.0 | fabs(c3) > 1.0 | fabs(c4) > 1.0);
-    if (zero_div)
-        atomicMin(&a.stats->first_zero_division, row);
-    if (domain)
-        atomicMin(&a.stats->first_domain_error, row);
+    // Rare rows, classified out of line (a branch that is almost never taken):
+    //  * a zero-length segment (ZeroDivisionError upstream, point.py:40) -- a length of 0, or a chain that is no longer
+    //    finite although its target is (a NaN target gives NaN angles without an exception upstream);
+    //  * a cosine outside [-1, 1] after the rounding (ValueError from acos upstream).
+    bool zero_div = false;
+    if (odd) {
+        const bool finite_t = isfinite(Tr + Tz);
+        const bool finite_c = isfinite(c2 + c3 + c4);
+        zero_div = finite_t & (!finite_c | (n_ce == 0.0) | (rc.seed_ab == 0.0) | !isfinite(r3 + z3));
+        if (zero_div)
+            atomicMin(&a.stats->first_zero_division, row);
+        else if (finite_c)
+            atomicMin(&a.stats->first_domain_error, row);
+    }
     if (a.iters)
         a.iters[idx] = k;
+    double x = 0, y = 0, z = 0;
+    if (FUSE_FK)  // small batches only (one launch instead of two): the error needs the target itself
+        ikb_load_xyz(a.xyz, a.xyz_f64, idx, x, y, z);
     if (OUT32 && IKB_FABRIK_TAIL32) {
-        // float32 buffer: the trigonometric tail on the fp32 pipe (see acos_f32)
-        float t0 = atan2_unit_f32(flip ? -uy : uy, flip ? -ux : ux);
+        // float32 buffer: the trigonometric tail on the fp32 pipe (see acos_f32).  theta_1 of the target's plane was
+        // evaluated when the target was staged; an effector on the far side of the z axis turns it by pi.
+        float t0 = (float)th1;
+        t0 = flip ? t0 - copysignf(IKB_PI_F, t0) : t0;
         t0 = r3 == 0.0 ? 0.0f : (r3 != r3 ? __int_as_float(0x7fc00000) : t0);
         const float acos2 = acos_f32(c2), acos3 = acos_f32(c3), acos4 = acos_f32(c4);
         float t1 = elbow_neg ? 1.5f * IKB_PI_F - acos2 : -(0.5f * IKB_PI_F - acos2);     // :82-85
@@ -394,7 +431,8 @@ __device__ __forceinline__ void fabrik_epilogue(const FabrikArgs &a, int idx, in
         return;
     }
     double th[4];
-    th[0] = atan2_unit(flip ? -uy : uy, flip ? -ux : ux);  // one evaluation: the compiler will not merge two calls under a select
+    th[0] = (double)th1;
+    th[0] = flip ? th[0] - copysign(PI, th[0]) : th[0];
     th[0] = r3 == 0.0 ? 0.0 : (r3 != r3 ? r3 : th[0]);
     const double acos2 = acos_fast(c2);
     th[1] = elbow_neg ? (3 * PI / 2) - acos2 : -(PI / 2 - acos2);  // :82-85
@@ -426,37 +464,41 @@ __device__ __forceinline__ void fabrik_epilogue(const FabrikArgs &a, int idx, in
     }
 }
 
-// OUT_Q: parked-chain ring; < 32 entries wait when a pass starts and a pass parks at most 32 per chain slot
-template <typename Real, int OUT_Q>
+// Per-warp queues in shared memory (one struct per warp: every access is "warp base + constant + slot").
+//   in_*  : staged reachable targets waiting for a free lane (ring)
+//   out_* : parked solved chains waiting for a full-width angle extraction (ring): < 32 wait when a pass starts and a
+//           pass parks at most 32
+//   far_* : staged out-of-reach targets waiting for a lockstep batch of 64 (always at the front of the arrays)
+#define IKB_OUT_Q 64
+#define IKB_FAR_BATCH 64
+#define IKB_FAR_Q (IKB_FAR_BATCH + 32)
+template <typename Real, typename Th1>
 struct WarpQueues {
-    int in_idx[IKB_Q];
     Real in_tr[IKB_Q], in_tz[IKB_Q];
-    int out_idx[OUT_Q];
-    int out_k[OUT_Q];  // iterations; bit 30 set when the chain stopped on max_iter, not on the tolerance
-    Real out_c[4][OUT_Q];
-    double fk_sum[32];  // per-lane sums of the fused FK error (kept out of the register file)
-    unsigned fk_cnt[32];
+    Real out_c[6][IKB_OUT_Q];  // r1, z1, r2, z2, Tr, Tz
+    Real far_tr[IKB_FAR_Q], far_tz[IKB_FAR_Q];
+    Th1 in_th1[IKB_Q], out_th1[IKB_OUT_Q], far_th1[IKB_FAR_Q];
+    int in_idx[IKB_Q], in_k0[IKB_Q];
+    int out_idx[IKB_OUT_Q], out_k[IKB_OUT_Q];
+    int far_idx[IKB_FAR_Q], far_k0[IKB_FAR_Q];
 };
 
-#define IKB_CAPPED_BIT 0x40000000
-
-// CHAINS = independent chains per lane.  The pass is one long dependency chain (every instruction
-// needs the previous result), so a second chain per lane doubles the instruction-level parallelism a
-// warp offers the FP64 pipe; its cost is registers (fewer resident warps).
-template <typename Real, int CHAINS, bool FUSE_FK, bool OUT32>
-__device__ __forceinline__ void fabrik_refill_loop(const FabrikArgs &a, WarpQueues<Real, 32 + 32 * CHAINS> *s_queues)
+// One warp's whole job: ONE scan of the input through a global chunk counter; every staged target is classified
+// (is_far) and queued for one of two pass loops that the warp alternates between:
+//   * reachable targets -> LANE REFILL: one chain per lane; a lane that converges parks its chain and takes the next
+//     staged target in the same step, so the pass loop runs at full width until 32 parked chains are ready for the
+//     angle extraction or the staged targets run low;
+//   * out-of-reach targets -> LOCKSTEP: batches of 64 (two chains per lane for instruction-level parallelism) run
+//     exactly max_iter passes without verdict, vote or parking, while the warp's reachable chains wait in registers.
+// The input rows of the NEXT staging step are loaded before the pass loop and consumed after it (their latency is
+// hidden behind the passes).
+template <typename Real, bool FUSE_FK, bool OUT32>
+__device__ __forceinline__ void fabrik_warp_loop(const FabrikArgs &a, WarpQueues<Real, typename TailType<OUT32>::type> *s_queues)
 {
-    // per-warp rings: input queue (pre-staged targets) and output queue (parked solved chains);
-    // one struct per warp so every access is "warp base + constant + slot"
-    constexpr int OUT_Q = 32 + 32 * CHAINS;
-
+    using Th1 = typename TailType<OUT32>::type;
     const int lane = threadIdx.x & 31;
-    WarpQueues<Real, OUT_Q> &q = s_queues[threadIdx.x >> 5];
+    WarpQueues<Real, Th1> &q = s_queues[threadIdx.x >> 5];
     const unsigned lt = ikb_lanemask_lt();
-    if (FUSE_FK) {
-        q.fk_sum[lane] = 0.0;
-        q.fk_cnt[lane] = 0u;
-    }
     const IkbRobot &rc = a.rc;
     const Real R0 = (Real)rc.seed_r[0], Z0 = (Real)rc.seed_z[0];
     const LinkScale<Real> d1(rc.link_k[1]), d2(rc.link_k[2]);
@@ -464,160 +506,239 @@ __device__ __forceinline__ void fabrik_refill_loop(const FabrikArgs &a, WarpQueu
     const int max_iter = rc.max_iter;
     const bool zero_iter = rc.zero_iter != 0;
 
-    bool active[CHAINS], exhausted = false;
-    unsigned active_mask[CHAINS];  // warp-uniform copies of `active`
-    int idx[CHAINS], k[CHAINS];
-    Real Tr[CHAINS], Tz[CHAINS];
-    PlanarChain<Real> c[CHAINS];
-#pragma unroll
-    for (int u = 0; u < CHAINS; ++u) {
-        active[u] = false; active_mask[u] = 0; idx[u] = 0; k[u] = 0; Tr[u] = 0; Tz[u] = 0;
-        c[u] = PlanarChain<Real>{0, 0, 0, 0};
-    }
+    // lane-refill state: one chain per lane
+    bool active = false;
+    unsigned active_mask = 0;  // warp-uniform copy of `active`
+    int idx = 0, k = 0;
+    Real Tr = 0, Tz = 0;
+    Th1 th1 = 0;
+    PlanarChain<Real> c{0, 0, 0, 0};
+    int in_head = 0, in_cnt = 0, out_head = 0, out_cnt = 0, far_cnt = 0;
+    // input scan
     long long cur = 0, cur_end = 0;
-    int in_head = 0, in_cnt = 0, out_head = 0, out_cnt = 0;
+    bool exhausted = false;
+    double px = 0, py = 0, pz = 0;  // prefetched rows cur - pf_m .. cur - 1 (lane l holds row pf_row)
+    long long pf_row = 0;
+    int pf_m = 0;                   // 0: no more input
     unsigned long long iters_local = 0;
     unsigned solved_local = 0, capped_local = 0;
+    double fk_sum = 0.0;
+    unsigned fk_cnt = 0;
 
+    auto prefetch = [&]() {
+        if (cur == cur_end && !exhausted) {
+            unsigned long long base = 0;
+            if (lane == 0)
+                base = atomicAdd(a.work_counter, (unsigned long long)IKB_FABRIK_CHUNK);
+            base = __shfl_sync(IKB_FULL_MASK, base, 0);
+            if ((long long)base >= a.n) {
+                exhausted = true;
+            } else {
+                cur = (long long)base;
+                cur_end = min(cur + IKB_FABRIK_CHUNK, a.n);
+            }
+        }
+        pf_m = exhausted ? 0 : (int)min((long long)32, cur_end - cur);
+        pf_row = cur + lane;
+        if (lane < pf_m)
+            ikb_load_xyz(a.xyz, a.xyz_f64, pf_row, px, py, pz);
+        cur += pf_m;
+    };
+
+    // classify the prefetched rows and queue them (full warp width): workspace limits (inverse.py:26-35), the
+    // in-plane radius, theta_1 of the target's plane, reachable / out of reach
+    auto stage = [&]() {
+        const bool valid = lane < pf_m;
+        if (valid && ikb_out_of_limits(rc, px, py, pz))
+            atomicMin(&a.stats->first_out_of_limits, a.index_base + pf_row);
+        double ux, uy;
+        const Real tr = (Real)planar_radius(px, py, ux, uy);
+        Th1 t1;
+        if (OUT32 && IKB_FABRIK_TAIL32)
+            t1 = (Th1)atan2_unit_f32(uy, ux);
+        else
+            t1 = (Th1)atan2_unit(uy, ux);
+        const int k0 = ux == 0.0 ? IKB_UXZERO_BIT : 0;
+        const bool far = valid && a.far_thr2 > 0.0 && is_far(px, py, pz, rc.seed_r[0], rc.seed_z[0], a.far_thr2);
+        const bool near = valid && !far;
+        const unsigned keep_n = __ballot_sync(IKB_FULL_MASK, near), keep_f = __ballot_sync(IKB_FULL_MASK, far);
+        if (near) {
+            const int slot = (in_head + in_cnt + __popc(keep_n & lt)) & (IKB_Q - 1);
+            q.in_idx[slot] = (int)pf_row; q.in_k0[slot] = k0;
+            q.in_tr[slot] = tr; q.in_tz[slot] = (Real)pz; q.in_th1[slot] = t1;
+        }
+        if (far) {
+            const int slot = far_cnt + __popc(keep_f & lt);
+            q.far_idx[slot] = (int)pf_row; q.far_k0[slot] = k0;
+            q.far_tr[slot] = tr; q.far_tz[slot] = (Real)pz; q.far_th1[slot] = t1;
+        }
+        in_cnt += __popc(keep_n);
+        far_cnt += __popc(keep_f);
+        __syncwarp();
+    };
+
+    // angle extraction on a full warp of parked chains (or on the remainder once everything else is done)
+    auto drain = [&](bool final) {
+        while (out_cnt >= 32 || (final && out_cnt > 0)) {
+            const int n_take = min(32, out_cnt);
+            if (lane < n_take) {
+                const int slot = (out_head + lane) & (IKB_OUT_Q - 1);
+                const int k_raw = q.out_k[slot];
+                fabrik_epilogue<FUSE_FK, OUT32, sizeof(Real) == 8, Th1>(a, q.out_idx[slot], k_raw, (double)q.out_c[0][slot],
+                                                     (double)q.out_c[1][slot], (double)q.out_c[2][slot],
+                                                     (double)q.out_c[3][slot], (double)q.out_c[4][slot],
+                                                     (double)q.out_c[5][slot], q.out_th1[slot], fk_sum, fk_cnt);
+                iters_local += (unsigned)(k_raw & IKB_K_MASK);
+                ++solved_local;
+                capped_local += (k_raw & IKB_CAPPED_BIT) ? 1u : 0u;
+            }
+            out_head = (out_head + n_take) & (IKB_OUT_Q - 1);
+            out_cnt -= n_take;
+            __syncwarp();
+        }
+    };
+
+    // one lockstep batch of up to 64 out-of-reach targets: chain slot u of lane l takes entry u * 32 + l; empty
+    // slots run on a harmless dummy target
+    auto far_batch = [&]() {
+        const int nb = min(far_cnt, IKB_FAR_BATCH);
+        PlanarChain<Real> fc[2];
+        Real fTr[2], fTz[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int e = u * 32 + lane;
+            fTr[u] = e < nb ? q.far_tr[e] : (Real)100;
+            fTz[u] = e < nb ? q.far_tz[e] : (Real)100;
+            fc[u].r1 = (Real)rc.seed_r[1]; fc[u].z1 = (Real)rc.seed_z[1];
+            fc[u].r2 = (Real)rc.seed_r[2]; fc[u].z2 = (Real)rc.seed_z[2];
+        }
+#pragma unroll 1
+        for (int it = 0; it < max_iter; ++it) {
+#pragma unroll
+            for (int u = 0; u < 2; ++u)
+                (void)fabrik_pass(fc[u], fTr[u], fTz[u], R0, Z0, d1, d2, start_band, goal_band);
+        }
+        // park 32 chains at a time behind whatever the lane-refill loop has parked, extract angles at full width
+        // (unrolled: a rolled loop keeps both chain sets live across the angle extraction and pushes spills into
+        //  the lane-refill pass loop)
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int cnt_u = max(0, min(32, nb - 32 * u));
+            if (lane < cnt_u) {
+                const int e = u * 32 + lane;
+                const int slot = (out_head + out_cnt + lane) & (IKB_OUT_Q - 1);
+                q.out_idx[slot] = q.far_idx[e];
+                q.out_k[slot] = max_iter | IKB_CAPPED_BIT | q.far_k0[e];
+                q.out_c[0][slot] = fc[u].r1; q.out_c[1][slot] = fc[u].z1;
+                q.out_c[2][slot] = fc[u].r2; q.out_c[3][slot] = fc[u].z2;
+                q.out_c[4][slot] = fTr[u]; q.out_c[5][slot] = fTz[u];
+                q.out_th1[slot] = q.far_th1[e];
+            }
+            out_cnt += cnt_u;
+            __syncwarp();
+            drain(false);
+        }
+        // move the rest (< 32 entries) to the front
+        const int rest = far_cnt - nb;
+        int m_idx = 0, m_k0 = 0;
+        Real m_tr = 0, m_tz = 0;
+        Th1 m_th1 = 0;
+        if (lane < rest) {
+            m_idx = q.far_idx[nb + lane]; m_k0 = q.far_k0[nb + lane];
+            m_tr = q.far_tr[nb + lane]; m_tz = q.far_tz[nb + lane]; m_th1 = q.far_th1[nb + lane];
+        }
+        __syncwarp();
+        if (lane < rest) {
+            q.far_idx[lane] = m_idx; q.far_k0[lane] = m_k0;
+            q.far_tr[lane] = m_tr; q.far_tz[lane] = m_tz; q.far_th1[lane] = m_th1;
+        }
+        __syncwarp();
+        far_cnt = rest;
+    };
+
+    auto take_target = [&](int slot) {
+        idx = q.in_idx[slot];
+        k = q.in_k0[slot];
+        Tr = q.in_tr[slot];
+        Tz = q.in_tz[slot];
+        th1 = q.in_th1[slot];
+        c.r1 = (Real)rc.seed_r[1]; c.z1 = (Real)rc.seed_z[1];
+        c.r2 = (Real)rc.seed_r[2]; c.z2 = (Real)rc.seed_z[2];
+    };
+
+    prefetch();
     for (;;) {
-        // 1. top up the input queue: one coalesced full-warp load of up to 32 targets
-        if (in_cnt <= 32 && !exhausted) {
-            if (cur == cur_end) {
-                unsigned long long base = 0;
-                if (lane == 0)
-                    base = atomicAdd(a.work_counter, (unsigned long long)IKB_FABRIK_CHUNK);
-                base = __shfl_sync(IKB_FULL_MASK, base, 0);
-                if ((long long)base >= a.n) {
-                    exhausted = true;
-                } else {
-                    cur = (long long)base;
-                    cur_end = min(cur + IKB_FABRIK_CHUNK, a.n);
-                }
-            }
-            if (!exhausted) {
-                const int m = (int)min((long long)32, cur_end - cur);
-                double x = 0, y = 0, z = 0, ux, uy;
-                bool mine = lane < m;
-                if (mine) {
-                    ikb_load_xyz(a.xyz, a.xyz_f64, cur + lane, x, y, z);
-                    if (a.far_thr2 > 0.0)
-                        mine = !is_far(x, y, z, rc.seed_r[0], rc.seed_z[0], a.far_thr2);
-                }
-                const unsigned keep = __ballot_sync(IKB_FULL_MASK, mine);
-                if (mine) {
-                    const int slot = (in_head + in_cnt + __popc(keep & lt)) & (IKB_Q - 1);
-                    q.in_idx[slot] = (int)(cur + lane);
-                    q.in_tr[slot] = (Real)planar_radius(x, y, ux, uy);
-                    q.in_tz[slot] = (Real)z;
-                }
-                in_cnt += __popc(keep);
-                cur += m;
-                __syncwarp();
-            }
+        // 1. stage input until the reachable queue is more than half full (or the input ends); a lockstep batch runs
+        //    whenever 64 out-of-reach targets are waiting, and once more for the remainder at the end of the input
+        for (;;) {
+            if (far_cnt >= IKB_FAR_BATCH || (pf_m == 0 && far_cnt > 0))
+                far_batch();
+            if (pf_m == 0 || in_cnt > IKB_Q - 32)
+                break;
+            stage();
+            prefetch();
         }
-        // 2. idle chain slots take the next staged targets
-        unsigned any_active = 0;
-#pragma unroll
-        for (int u = 0; u < CHAINS; ++u) {
-            if (active_mask[u] != IKB_FULL_MASK && in_cnt > 0) {
-                const unsigned need = ~active_mask[u];
-                const int rank = __popc(need & lt);
-                if (!active[u] && rank < in_cnt) {
-                    const int slot = (in_head + rank) & (IKB_Q - 1);
-                    idx[u] = q.in_idx[slot];
-                    Tr[u] = q.in_tr[slot];
-                    Tz[u] = q.in_tz[slot];
-                    c[u].r1 = (Real)rc.seed_r[1]; c[u].z1 = (Real)rc.seed_z[1];
-                    c[u].r2 = (Real)rc.seed_r[2]; c[u].z2 = (Real)rc.seed_z[2];
-                    k[u] = 0;
-                    active[u] = true;
-                }
-                const int take = min(__popc(need), in_cnt);
-                in_head = (in_head + take) & (IKB_Q - 1);
-                in_cnt -= take;
-                active_mask[u] = __ballot_sync(IKB_FULL_MASK, active[u]);
+        // 2. idle lanes take staged targets (start-up, and after the queue ran dry)
+        if (active_mask != IKB_FULL_MASK && in_cnt > 0) {
+            const unsigned need = ~active_mask;
+            const int rank = __popc(need & lt);
+            if (!active && rank < in_cnt) {
+                take_target((in_head + rank) & (IKB_Q - 1));
+                active = true;
             }
-            any_active |= active_mask[u];
+            const int take = min(__popc(need), in_cnt);
+            in_head = (in_head + take) & (IKB_Q - 1);
+            in_cnt -= take;
+            active_mask = __ballot_sync(IKB_FULL_MASK, active);
         }
-        // 3. FABRIK passes (reference fabrik.py:57-65).  Every lane executes the pass -- chain slots without
-        //    a live chain compute on stale registers and are ignored -- so the loop body is branch-free;
-        //    a chain that finishes is parked at once and the warp only leaves the loop when enough slots
-        //    idle to make a refill worthwhile or a full warp of parked chains is ready.
-        if (any_active != 0) {
-            const int idle_limit = (exhausted && in_cnt == 0) ? 32 * CHAINS + 1 : IKB_FABRIK_IDLE_T * CHAINS;
-            int n_idle = 0;
-#pragma unroll
-            for (int u = 0; u < CHAINS; ++u)
-                n_idle += 32 - __popc(active_mask[u]);
+        // 3. FABRIK passes (reference fabrik.py:57-65).  Every lane executes the pass -- lanes without a live chain
+        //    compute on stale registers and are ignored -- so the loop body is branch-free; a chain that finishes is
+        //    parked and its lane takes the next staged target at once.  The warp leaves the loop when a full warp of
+        //    parked chains is ready, when the staged targets run low while there is input left, or when no lane is live.
+        if (active_mask != 0) {
             bool leave = false;
             do {
-                bool more[CHAINS], fin[CHAINS];
-                unsigned m[CHAINS], many = 0;
-#pragma unroll
-                for (int u = 0; u < CHAINS; ++u) {
-                    more[u] = false;
-                    if (!zero_iter) {
-                        more[u] = fabrik_pass(c[u], Tr[u], Tz[u], R0, Z0, d1, d2, start_band, goal_band);
-                        ++k[u];
-                    }
+                bool more = false;
+                if (!zero_iter) {
+                    more = fabrik_pass(c, Tr, Tz, R0, Z0, d1, d2, start_band, goal_band);
+                    ++k;
                 }
-#pragma unroll
-                for (int u = 0; u < CHAINS; ++u) {
-                    fin[u] = active[u] & (!more[u] | (k[u] >= max_iter));
-                    m[u] = __ballot_sync(IKB_FULL_MASK, fin[u]);
-                    many |= m[u];
-                }
-                if (many != 0) {
-#pragma unroll
-                    for (int u = 0; u < CHAINS; ++u) {
-                        if (m[u] != 0) {
-                            if (fin[u]) {
-                                int slot = out_head + out_cnt + __popc(m[u] & lt);
-                                slot -= slot >= OUT_Q ? OUT_Q : 0;
-                                q.out_idx[slot] = idx[u];
-                                q.out_k[slot] = more[u] ? (k[u] | IKB_CAPPED_BIT) : k[u];
-                                q.out_c[0][slot] = c[u].r1; q.out_c[1][slot] = c[u].z1;
-                                q.out_c[2][slot] = c[u].r2; q.out_c[3][slot] = c[u].z2;
-                                active[u] = false;
-                            }
-                            const int nf = __popc(m[u]);
-                            out_cnt += nf;
-                            n_idle += nf;
-                            active_mask[u] &= ~m[u];
-                        }
+                const bool fin = active & (!more | ((k & IKB_K_MASK) >= max_iter));
+                const unsigned m = __ballot_sync(IKB_FULL_MASK, fin);
+                if (m != 0) {
+                    const int rank = __popc(m & lt), nf = __popc(m);
+                    if (fin) {
+                        const int slot = (out_head + out_cnt + rank) & (IKB_OUT_Q - 1);
+                        q.out_idx[slot] = idx;
+                        q.out_k[slot] = more ? (k | IKB_CAPPED_BIT) : k;
+                        q.out_c[0][slot] = c.r1; q.out_c[1][slot] = c.z1;
+                        q.out_c[2][slot] = c.r2; q.out_c[3][slot] = c.z2;
+                        q.out_c[4][slot] = Tr; q.out_c[5][slot] = Tz;
+                        q.out_th1[slot] = th1;
+                        if (rank < in_cnt)
+                            take_target((in_head + rank) & (IKB_Q - 1));
+                        else
+                            active = false;
                     }
-                    any_active = 0;
-#pragma unroll
-                    for (int u = 0; u < CHAINS; ++u)
-                        any_active |= active_mask[u];
-                    // the parked-chain ring holds IKB_Q entries: leave as soon as one more pass could overflow it
-                    leave = (n_idle >= idle_limit) | (out_cnt >= 32) | (any_active == 0);
+                    out_cnt += nf;
+                    if (nf > in_cnt) {  // warp-uniform: some lanes found the queue empty
+                        in_head = (in_head + in_cnt) & (IKB_Q - 1);
+                        in_cnt = 0;
+                        active_mask = __ballot_sync(IKB_FULL_MASK, active);
+                    } else {
+                        in_head = (in_head + nf) & (IKB_Q - 1);
+                        in_cnt -= nf;
+                    }
+                    leave = (out_cnt >= 32) | (active_mask == 0) | ((pf_m > 0) & (in_cnt < IKB_FABRIK_LOW_WATER));
                 }
             } while (!leave);
             __syncwarp();
         }
-        // 4. the fp64 epilogue runs on a full warp of parked chains (or on the remainder once all
-        //    work is done).  ONE call site: every row goes through the same instruction sequence,
-        //    so results do not depend on where in the batch a target sits.
-        const bool drained = any_active == 0 && exhausted && in_cnt == 0;
-        while (out_cnt >= 32 || (drained && out_cnt > 0)) {
-            const int n_take = min(32, out_cnt);
-            if (lane < n_take) {
-                int slot = out_head + lane;
-                slot -= slot >= OUT_Q ? OUT_Q : 0;
-                const int k_raw = q.out_k[slot], k_done = k_raw & (IKB_CAPPED_BIT - 1);
-                fabrik_epilogue<FUSE_FK, OUT32>(a, q.out_idx[slot], k_done, (double)q.out_c[0][slot], (double)q.out_c[1][slot],
-                                (double)q.out_c[2][slot], (double)q.out_c[3][slot], q.fk_sum[lane], q.fk_cnt[lane]);
-                iters_local += (unsigned)k_done;
-                ++solved_local;
-                capped_local += (k_raw & IKB_CAPPED_BIT) ? 1u : 0u;
-            }
-            out_head += n_take;
-            out_head -= out_head >= OUT_Q ? OUT_Q : 0;
-            out_cnt -= n_take;
-            __syncwarp();
-        }
-        if (drained && out_cnt == 0)
+        // 4. angle extraction at full width.  Same instruction sequence for every row of a launch, so results do not
+        //    depend on where in the batch a target sits.
+        const bool final = pf_m == 0 && in_cnt == 0 && far_cnt == 0 && active_mask == 0;
+        drain(final);
+        if (final)
             break;
     }
     // statistics: one atomic per warp and counter
@@ -630,8 +751,8 @@ __device__ __forceinline__ void fabrik_refill_loop(const FabrikArgs &a, WarpQueu
             atomicAdd(&a.stats->n_iter_capped, (unsigned long long)cp);
     }
     if (FUSE_FK) {
-        const double es = ikb_warp_sum(q.fk_sum[lane]);
-        const unsigned ec = ikb_warp_sum(q.fk_cnt[lane]);
+        const double es = ikb_warp_sum(fk_sum);
+        const unsigned ec = ikb_warp_sum(fk_cnt);
         if (lane == 0 && ec != 0) {
             atomicAdd(&a.stats->sum_fk_error, es);
             atomicAdd(&a.stats->n_fk_error, (unsigned long long)ec);
@@ -639,154 +760,11 @@ __device__ __forceinline__ void fabrik_refill_loop(const FabrikArgs &a, WarpQueu
     }
 }
 
-template <typename Real, int CHAINS, bool FUSE_FK, bool OUT32>
-__global__ void __launch_bounds__(IKB_FABRIK_WARPS * 32, (CHAINS == 1 ? IKB_FABRIK_MIN_CTAS : IKB_FABRIK_MIN_CTAS2))
-    fabrik_planar_kernel(const FabrikArgs a)
+template <typename Real, bool FUSE_FK, bool OUT32>
+__global__ void __launch_bounds__(IKB_FABRIK_WARPS * 32, IKB_FABRIK_MIN_CTAS) fabrik_planar_kernel(const FabrikArgs a)
 {
-    __shared__ WarpQueues<Real, 32 + 32 * CHAINS> s_queues[IKB_FABRIK_WARPS];
-    fabrik_refill_loop<Real, CHAINS, FUSE_FK, OUT32>(a, s_queues);
-}
-
-// ---- out-of-reach targets: max_iter passes in lockstep (see is_far) -----------------------------------------
-#ifndef IKB_FAR_CHAINS
-#define IKB_FAR_CHAINS 2
-#endif
-#ifndef IKB_FAR_MIN_CTAS
-#define IKB_FAR_MIN_CTAS 3
-#endif
-
-template <typename Real>
-struct FarQueue {
-    int idx[32 * IKB_FAR_CHAINS + 32];
-    Real tr[32 * IKB_FAR_CHAINS + 32], tz[32 * IKB_FAR_CHAINS + 32];
-    Real out_c[4][32 * IKB_FAR_CHAINS];
-};
-
-template <typename Real, bool OUT32>
-__device__ __forceinline__ void fabrik_far_loop(const FabrikArgs &a, FarQueue<Real> *s_q)
-{
-    constexpr int CH = IKB_FAR_CHAINS, BATCH = 32 * CH;
-    FarQueue<Real> &q = s_q[threadIdx.x >> 5];
-    const int lane = threadIdx.x & 31;
-    const unsigned lt = ikb_lanemask_lt();
-    const IkbRobot &rc = a.rc;
-    const Real R0 = (Real)rc.seed_r[0], Z0 = (Real)rc.seed_z[0];
-    const LinkScale<Real> d1(rc.link_k[1]), d2(rc.link_k[2]);
-    const Band<Real> start_band = make_band<Real>(rc, 0), goal_band = make_band<Real>(rc, 1);
-    const int max_iter = rc.max_iter;
-    long long cur = 0, cur_end = 0;
-    int cnt = 0;  // queued targets, always at the front of the arrays
-    bool exhausted = false;
-    unsigned solved_local = 0;
-    double fk_sum = 0.0;
-    unsigned fk_cnt = 0;
-    for (;;) {
-        // stage far targets until a full batch is queued (or the input is exhausted)
-        while (cnt < BATCH && !exhausted) {
-            if (cur == cur_end) {
-                unsigned long long base = 0;
-                if (lane == 0)
-                    base = atomicAdd(a.work_counter_far, (unsigned long long)IKB_FABRIK_CHUNK);
-                base = __shfl_sync(IKB_FULL_MASK, base, 0);
-                if ((long long)base >= a.n) {
-                    exhausted = true;
-                    break;
-                }
-                cur = (long long)base;
-                cur_end = min(cur + IKB_FABRIK_CHUNK, a.n);
-            }
-            const int m = (int)min((long long)32, cur_end - cur);
-            double x = 0, y = 0, z = 0, ux, uy;
-            bool mine = false;
-            if (lane < m) {
-                ikb_load_xyz(a.xyz, a.xyz_f64, cur + lane, x, y, z);
-                mine = is_far(x, y, z, rc.seed_r[0], rc.seed_z[0], a.far_thr2);
-            }
-            const unsigned keep = __ballot_sync(IKB_FULL_MASK, mine);
-            if (mine) {
-                const int slot = cnt + __popc(keep & lt);
-                q.idx[slot] = (int)(cur + lane);
-                q.tr[slot] = (Real)planar_radius(x, y, ux, uy);
-                q.tz[slot] = (Real)z;
-            }
-            cnt += __popc(keep);
-            cur += m;
-            __syncwarp();
-        }
-        if (cnt == 0)
-            break;
-        // one batch: chain slot u of lane l takes entry u * 32 + l; empty slots run on a harmless dummy target
-        const int nb = min(cnt, BATCH);
-        PlanarChain<Real> c[CH];
-        Real Tr[CH], Tz[CH];
-#pragma unroll
-        for (int u = 0; u < CH; ++u) {
-            const int e = u * 32 + lane;
-            Tr[u] = e < nb ? q.tr[e] : (Real)100;
-            Tz[u] = e < nb ? q.tz[e] : (Real)100;
-            c[u].r1 = (Real)rc.seed_r[1]; c[u].z1 = (Real)rc.seed_z[1];
-            c[u].r2 = (Real)rc.seed_r[2]; c[u].z2 = (Real)rc.seed_z[2];
-        }
-#pragma unroll 1
-        for (int it = 0; it < max_iter; ++it) {
-#pragma unroll
-            for (int u = 0; u < CH; ++u)
-                (void)fabrik_pass(c[u], Tr[u], Tz[u], R0, Z0, d1, d2, start_band, goal_band);
-        }
-        // park the chains, then ONE epilogue call site for every entry (results must not depend on the chain slot)
-#pragma unroll
-        for (int u = 0; u < CH; ++u) {
-            const int e = u * 32 + lane;
-            q.out_c[0][e] = c[u].r1; q.out_c[1][e] = c[u].z1; q.out_c[2][e] = c[u].r2; q.out_c[3][e] = c[u].z2;
-        }
-        __syncwarp();
-#pragma unroll 1
-        for (int e = lane; e < nb; e += 32) {
-            fabrik_epilogue<false, OUT32>(a, q.idx[e], max_iter, (double)q.out_c[0][e], (double)q.out_c[1][e],
-                                   (double)q.out_c[2][e], (double)q.out_c[3][e], fk_sum, fk_cnt);
-            ++solved_local;
-        }
-        __syncwarp();
-        // move the rest (< 32 entries) to the front
-        const int rest = cnt - nb;
-        int m_idx = 0;
-        Real m_tr = 0, m_tz = 0;
-        if (lane < rest) { m_idx = q.idx[nb + lane]; m_tr = q.tr[nb + lane]; m_tz = q.tz[nb + lane]; }
-        __syncwarp();
-        if (lane < rest) { q.idx[lane] = m_idx; q.tr[lane] = m_tr; q.tz[lane] = m_tz; }
-        __syncwarp();
-        cnt = rest;
-    }
-    const unsigned sv = ikb_warp_sum(solved_local);
-    if (lane == 0 && sv != 0) {
-        atomicAdd(&a.stats->sum_iterations, (unsigned long long)sv * (unsigned long long)max_iter);
-        atomicAdd(&a.stats->n_solved, (unsigned long long)sv);
-        atomicAdd(&a.stats->n_iter_capped, (unsigned long long)sv);
-    }
-}
-
-// One launch for both populations: a CTA starts in one role and, when the rows of its role are used up, carries on
-// in the other, so the two populations balance themselves whatever the mix.  Each role scans the whole input through
-// its own chunk counter and claims its rows with is_far.  (Which role a CTA starts in hardly matters -- 17.1 to
-// 17.7 ms per 1e8 rows across 0..100 % -- because a lockstep warp is bound by the latency of its own dependent fp64
-// chain rather than by the pipe once fewer than six of them share a scheduler.)
-template <typename Real, bool OUT32>
-__global__ void __launch_bounds__(IKB_FABRIK_WARPS * 32, IKB_FABRIK_MIN_CTAS) fabrik_split_kernel(const FabrikArgs a)
-{
-    constexpr size_t kNear = sizeof(WarpQueues<Real, 64>) * IKB_FABRIK_WARPS, kFar = sizeof(FarQueue<Real>) * IKB_FABRIK_WARPS;
-    __shared__ __align__(16) unsigned char s_raw[kNear > kFar ? kNear : kFar];
-#ifndef IKB_SPLIT_FAR_PCT
-#define IKB_SPLIT_FAR_PCT 34
-#endif
-    const bool far_first = blockIdx.x * 100u < gridDim.x * (unsigned)IKB_SPLIT_FAR_PCT;
-#pragma unroll 1
-    for (int phase = 0; phase < 2; ++phase) {
-        if ((phase == 0) == far_first)
-            fabrik_far_loop<Real, OUT32>(a, reinterpret_cast<FarQueue<Real> *>(s_raw));
-        else
-            fabrik_refill_loop<Real, 1, false, OUT32>(a, reinterpret_cast<WarpQueues<Real, 64> *>(s_raw));
-        __syncthreads();  // the two roles overlay the same shared memory
-    }
+    extern __shared__ __align__(16) unsigned char s_raw[];
+    fabrik_warp_loop<Real, FUSE_FK, OUT32>(a, reinterpret_cast<WarpQueues<Real, typename TailType<OUT32>::type> *>(s_raw));
 }
 
 // ---- generic 3-D path ---------------------------------------------------------------------------
@@ -975,12 +953,27 @@ __global__ void __launch_bounds__(128) fabrik_generic_ikine_kernel(const FabrikG
 }  // namespace
 
 // ---- launchers (called from capi.cu) --------------------------------------------------------------
-// Rows below which the out-of-reach split is not worth a second launch.
-#ifndef IKB_SPLIT_MIN_ROWS
-#define IKB_SPLIT_MIN_ROWS 65536
-#endif
+namespace {
+template <typename Real, bool FUSE_FK, bool OUT32>
+cudaError_t launch_planar(const FabrikArgs &a, unsigned grid, cudaStream_t stream)
+{
+    constexpr size_t smem = sizeof(WarpQueues<Real, typename TailType<OUT32>::type>) * IKB_FABRIK_WARPS;
+    static const cudaError_t attr = cudaFuncSetAttribute(fabrik_planar_kernel<Real, FUSE_FK, OUT32>,
+                                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (attr != cudaSuccess)
+        return attr;
+    // three CTAs per SM need ~200 KB of shared memory: ask for the largest carve-out
+    static const cudaError_t carve = cudaFuncSetAttribute(fabrik_planar_kernel<Real, FUSE_FK, OUT32>,
+                                                          cudaFuncAttributePreferredSharedMemoryCarveout,
+                                                          (int)cudaSharedmemCarveoutMaxShared);
+    if (carve != cudaSuccess)
+        return carve;
+    fabrik_planar_kernel<Real, FUSE_FK, OUT32><<<grid, IKB_FABRIK_WARPS * 32, smem, stream>>>(a);
+    return cudaGetLastError();
+}
+}  // namespace
 
-// work_counter: TWO consecutive counters (lane-refill kernel, far kernel).
+// work_counter: the chunk counter of this launch (reset here).
 cudaError_t ikb_launch_fabrik_planar(const void *xyz, int xyz_f64, long long n, long long index_base,
                                      void *angles, int angles_f64, int *iters, void *fk_err, int fk_stats,
                                      int precision, IkbDeviceStats *stats, unsigned long long *work_counter,
@@ -993,48 +986,34 @@ cudaError_t ikb_launch_fabrik_planar(const void *xyz, int xyz_f64, long long n, 
     a.angles = angles; a.angles_f64 = angles_f64; a.iters = iters;
     a.fk_err = fk_err; a.fk_stats = fk_stats;
     a.stats = stats; a.work_counter = work_counter; a.rc = rc;
-    a.far_thr2 = -1.0;
-    a.work_counter_far = nullptr;
-    cudaError_t err = cudaMemsetAsync(work_counter, 0, 2 * sizeof(unsigned long long), stream);
+    cudaError_t err = cudaMemsetAsync(work_counter, 0, sizeof(unsigned long long), stream);
     if (err != cudaSuccess)
         return err;
     const bool fuse = fk_err != nullptr || fk_stats != 0;  // the caller checked rc.fk_planar_tail
+    // out-of-reach targets run in lockstep batches (see is_far); IKB_FABRIK_SPLIT=0 sends every target through the
+    // lane-refill loop instead (same arithmetic, value-identical results: tests/test_gpu_fabrik.py)
     static const bool split_enabled = [] { const char *v = std::getenv("IKB_FABRIK_SPLIT"); return !v || v[0] != '0'; }();
-    const bool split = split_enabled && !fuse && n >= IKB_SPLIT_MIN_ROWS && !rc.zero_iter && rc.max_iter >= 8;
-    // persistent grid: resident CTAs per SM x SM count, trimmed for small batches
-    const int per_cta = IKB_FABRIK_WARPS * 32;
-    long long want = (n + per_cta - 1) / per_cta;
-    long long grid = (long long)num_sms * (IKB_FABRIK_CHAINS == 1 ? IKB_FABRIK_MIN_CTAS : IKB_FABRIK_MIN_CTAS2);
-    if (want < grid)
-        grid = want;
-    if (split) {
+    a.far_thr2 = -1.0;
+    if (split_enabled && !rc.zero_iter && rc.max_iter >= 8) {
         const double reach = rc.links[1] + rc.links[2] + rc.links[3];
         const double thr = reach + rc.tol + 1e-6 * (1.0 + reach);  // margin >> the rounding of |f2 - S| <= d1 + d2
         a.far_thr2 = thr * thr;
-        a.work_counter_far = work_counter + 1;
-        const void *kargs[] = {&a};
-        const void *fn;
-        if (precision == IKB_FABRIK_F32)
-            fn = angles_f64 ? (const void *)fabrik_split_kernel<float, false> : (const void *)fabrik_split_kernel<float, true>;
-        else
-            fn = angles_f64 ? (const void *)fabrik_split_kernel<double, false> : (const void *)fabrik_split_kernel<double, true>;
-        return cudaLaunchKernel(fn, dim3((unsigned)grid), dim3(per_cta), const_cast<void **>(kargs), 0, stream);
     }
+    // persistent grid: resident CTAs per SM x SM count, trimmed for small batches
+    const int per_cta = IKB_FABRIK_WARPS * 32;
+    long long grid = (long long)num_sms * IKB_FABRIK_MIN_CTAS;
+    const long long want = (n + per_cta - 1) / per_cta;
+    if (want < grid)
+        grid = want;
     // kernel variant = (iterate precision, fused FK error, output precision); the trigonometric tail of the angle
     // extraction follows the output buffer's precision (see acos_f32)
-    const void *fn;
-#define IKB_PICK(REAL)                                                                                               \
-    (fuse ? (angles_f64 ? (const void *)fabrik_planar_kernel<REAL, IKB_FABRIK_CHAINS, true, false>                   \
-                        : (const void *)fabrik_planar_kernel<REAL, IKB_FABRIK_CHAINS, true, true>)                   \
-          : (angles_f64 ? (const void *)fabrik_planar_kernel<REAL, IKB_FABRIK_CHAINS, false, false>                  \
-                        : (const void *)fabrik_planar_kernel<REAL, IKB_FABRIK_CHAINS, false, true>))
-    if (precision == IKB_FABRIK_F32)
-        fn = IKB_PICK(float);
-    else
-        fn = IKB_PICK(double);
+#define IKB_PICK(REAL)                                                                           \
+    (fuse ? (angles_f64 ? launch_planar<REAL, true, false>(a, (unsigned)grid, stream)            \
+                        : launch_planar<REAL, true, true>(a, (unsigned)grid, stream))            \
+          : (angles_f64 ? launch_planar<REAL, false, false>(a, (unsigned)grid, stream)           \
+                        : launch_planar<REAL, false, true>(a, (unsigned)grid, stream)))
+    return precision == IKB_FABRIK_F32 ? IKB_PICK(float) : IKB_PICK(double);
 #undef IKB_PICK
-    const void *kargs[] = {&a};
-    return cudaLaunchKernel(fn, dim3((unsigned)grid), dim3(per_cta), const_cast<void **>(kargs), 0, stream);
 }
 
 cudaError_t ikb_launch_fabrik_generic_ikine(const void *xyz, int xyz_f64, long long n, long long index_base,

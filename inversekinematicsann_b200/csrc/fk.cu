@@ -121,6 +121,78 @@ __global__ void __launch_bounds__(256, FK_MINB) fk_kernel(const FkArgs a)
     }
 }
 
+// ---- the common case at HBM speed: fp32 buffers, closed-form arm, position error only ----------------------------------
+// The generic kernel above is bound by instruction issue (194 instructions per row, 69 % of the HBM roofline).  Here a
+// thread takes two ADJACENT rows per trip -- angles as two 16-byte loads, the six target floats as three 8-byte loads,
+// the two errors as one 8-byte store -- and evaluates the eight sin/cos pairs two at a time on the packed fp32 pipe
+// (ikb_sincos2: bit-identical to the scalar code, about half its instructions).  The chain arithmetic is the same inline
+// function as everywhere else, so the errors are the ones the generic kernel and the solvers' fused epilogues produce.
+#ifndef FK_PAIR_MINB
+#define FK_PAIR_MINB 4
+#endif
+__global__ void __launch_bounds__(256, FK_PAIR_MINB) fk_error_pairs_kernel(const FkArgs a)
+{
+    const long long n_pairs = a.n >> 1;  // the odd last row (if any) is handled by one thread after the loop
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const float *k = a.rc.fkc_f;
+    const float TWO_PI = 6.283185307179586f;
+    double err_sum = 0.0;
+    unsigned err_cnt = 0;
+    const float4 *ang = reinterpret_cast<const float4 *>(a.angles);
+    const float2 *tgt = reinterpret_cast<const float2 *>(a.targets);
+    float2 *out = reinterpret_cast<float2 *>(a.err_out);
+    auto row_error = [&](const float (&s)[4], const float (&c)[4], const float4 &th, float tx, float ty, float tz) {
+        float px, py, pz;
+        fk_planar_tail_position<float>(s, c, k[0], k[1], k[2], k[3], k[4], k[5], k[6], k[7], px, py, pz);
+        const float dx = px - tx, dy = py - ty, dz = pz - tz;
+        const float err = sqrt(dx * dx + dy * dy + dz * dz);
+        const bool ok = !(fabsf(th.x) > TWO_PI) & !(fabsf(th.y) > TWO_PI) & !(fabsf(th.z) > TWO_PI) & !(fabsf(th.w) > TWO_PI);
+        return ok ? err : __int_as_float(0x7fc00000);
+    };
+    for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < n_pairs; p += stride) {
+        const float4 th0 = __ldg(ang + 2 * p), th1 = __ldg(ang + 2 * p + 1);
+        const float2 t0 = __ldg(tgt + 3 * p), t1 = __ldg(tgt + 3 * p + 1), t2 = __ldg(tgt + 3 * p + 2);
+        float s0[4], c0[4], s1[4], c1[4];
+        ikb_sincos2(th0.x, th1.x, s0[0], c0[0], s1[0], c1[0]);
+        ikb_sincos2(th0.y, th1.y, s0[1], c0[1], s1[1], c1[1]);
+        ikb_sincos2(th0.z, th1.z, s0[2], c0[2], s1[2], c1[2]);
+        ikb_sincos2(th0.w, th1.w, s0[3], c0[3], s1[3], c1[3]);
+        const float e0 = row_error(s0, c0, th0, t0.x, t0.y, t1.x);
+        const float e1 = row_error(s1, c1, th1, t1.y, t2.x, t2.y);
+        if (e0 != e0)  // NaN from the angle guard of forward.py:23-25 (or from NaN input: then the row index is not recorded)
+            if (fabsf(th0.x) > TWO_PI || fabsf(th0.y) > TWO_PI || fabsf(th0.z) > TWO_PI || fabsf(th0.w) > TWO_PI)
+                atomicMin(&a.stats->first_fk_angle_range, a.index_base + 2 * p);
+        if (e1 != e1)
+            if (fabsf(th1.x) > TWO_PI || fabsf(th1.y) > TWO_PI || fabsf(th1.z) > TWO_PI || fabsf(th1.w) > TWO_PI)
+                atomicMin(&a.stats->first_fk_angle_range, a.index_base + 2 * p + 1);
+        if (out)
+            out[p] = make_float2(e0, e1);
+        float part = 0.f;
+        if (isfinite(e0)) { part += e0; ++err_cnt; }
+        if (isfinite(e1)) { part += e1; ++err_cnt; }
+        err_sum += (double)part;
+    }
+    if ((a.n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {  // the odd last row: scalar code, same arithmetic
+        const long long i = a.n - 1;
+        const float4 v = __ldg(ang + i);
+        const float th[4] = {v.x, v.y, v.z, v.w};
+        const float *t = reinterpret_cast<const float *>(a.targets) + 3 * i;
+        const float e = ikb_fk_error_planar_tail<float>(th, __ldg(t), __ldg(t + 1), __ldg(t + 2), k[0], k[1], k[2], k[3], k[4],
+                                                        k[5], k[6], k[7]);
+        if (e != e && (fabsf(v.x) > TWO_PI || fabsf(v.y) > TWO_PI || fabsf(v.z) > TWO_PI || fabsf(v.w) > TWO_PI))
+            atomicMin(&a.stats->first_fk_angle_range, a.index_base + i);
+        if (a.err_out)
+            reinterpret_cast<float *>(a.err_out)[i] = e;
+        if (isfinite(e)) { err_sum += (double)e; ++err_cnt; }
+    }
+    err_sum = ikb_warp_sum(err_sum);
+    err_cnt = ikb_warp_sum(err_cnt);
+    if ((threadIdx.x & 31) == 0 && err_cnt) {
+        atomicAdd(&a.stats->sum_fk_error, err_sum);
+        atomicAdd(&a.stats->n_fk_error, (unsigned long long)err_cnt);
+    }
+}
+
 // all four cumulative homogeneous matrices (forward.py:79-94), fp64, one thread per angle set
 __global__ void fk_chain_kernel(const double *angles, long long n, double *chain_out, int *status,
                                 const IkbRobot rc)
@@ -231,6 +303,16 @@ cudaError_t ikb_launch_fk(const void *angles, int angles_f64, long long n, long 
     a.angles = angles; a.angles_f64 = angles_f64; a.n = n; a.index_base = index_base;
     a.pos_out = pos_out; a.targets = targets; a.xyz_f64 = xyz_f64; a.err_out = err_out;
     a.stats = stats; a.rc = rc;
+    // fp32 buffers, closed-form arm with alpha inside the guard, error only, 8-byte aligned rows: the pair kernel
+    bool alpha_ok = rc.fk_planar_tail != 0;
+    for (int j = 0; j < 4; ++j)
+        alpha_ok = alpha_ok && !(rc.alpha[j] < -6.283185307179586) && !(rc.alpha[j] > 6.283185307179586);
+    if (!angles_f64 && !xyz_f64 && targets && !pos_out && alpha_ok && ((uintptr_t)targets & 7) == 0 &&
+        ((uintptr_t)err_out & 7) == 0 && n >= 2) {
+        const unsigned pgrid = ikb_stream_grid(n / 2, num_sms, 256, FK_PAIR_MINB);
+        fk_error_pairs_kernel<<<pgrid, 256, 0, stream>>>(a);
+        return cudaGetLastError();
+    }
     const unsigned grid = ikb_stream_grid(n, num_sms, 256, 8);
     if (angles_f64) {
         if (xyz_f64)

@@ -30,6 +30,69 @@ __device__ __forceinline__ void ikb_sincos(float x, float *s, float *c)
 }
 __device__ __forceinline__ void ikb_sincos(double x, double *s, double *c) { sincos(x, s, c); }
 
+// ---- two angles at a time on the packed fp32 pipe (sm_100: FFMA2 / FMUL2 / FADD2 = fma.rn.f32x2 ...) -----------------
+// Same operations in the same order as ikb_sincos(float), every one correctly rounded, so the results are bit-identical
+// to two scalar calls; what changes is the instruction count (15 packed + 12 select instructions for two angles instead
+// of 2 x 23), which is what bounds K3 (fk.cu) once the loads are vectorised.
+typedef unsigned long long ikb_f32x2;
+__device__ __forceinline__ ikb_f32x2 ikb_pack2(float lo, float hi)
+{
+    ikb_f32x2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void ikb_unpack2(ikb_f32x2 v, float &lo, float &hi)
+{
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ ikb_f32x2 ikb_dup2(float x) { return ikb_pack2(x, x); }
+__device__ __forceinline__ ikb_f32x2 ikb_fma2(ikb_f32x2 a, ikb_f32x2 b, ikb_f32x2 c)
+{
+    ikb_f32x2 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+__device__ __forceinline__ ikb_f32x2 ikb_mul2(ikb_f32x2 a, ikb_f32x2 b)
+{
+    ikb_f32x2 r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ ikb_f32x2 ikb_add2(ikb_f32x2 a, ikb_f32x2 b)
+{
+    ikb_f32x2 r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+
+__device__ __forceinline__ void ikb_sincos2(float x0, float x1, float &s0, float &c0, float &s1, float &c1)
+{
+    const ikb_f32x2 X = ikb_pack2(x0, x1);
+    const ikb_f32x2 T = ikb_fma2(X, ikb_dup2(0.63661977236758134f), ikb_dup2(12582912.0f));
+    float t0, t1;
+    ikb_unpack2(T, t0, t1);
+    const int q0 = __float_as_int(t0), q1 = __float_as_int(t1);
+    const ikb_f32x2 K = ikb_add2(T, ikb_dup2(-12582912.0f));
+    ikb_f32x2 R = ikb_fma2(K, ikb_dup2(-1.57079625129699707031f), X);
+    R = ikb_fma2(K, ikb_dup2(-7.54978941586159635335e-8f), R);
+    const ikb_f32x2 R2 = ikb_mul2(R, R);
+    ikb_f32x2 SP = ikb_fma2(R2, ikb_dup2(-1.9515295891e-4f), ikb_dup2(8.3321608736e-3f));
+    SP = ikb_fma2(SP, R2, ikb_dup2(-1.6666654611e-1f));
+    SP = ikb_fma2(ikb_mul2(SP, R2), R, R);
+    ikb_f32x2 CP = ikb_fma2(R2, ikb_dup2(2.443315711809948e-5f), ikb_dup2(-1.388731625493765e-3f));
+    CP = ikb_fma2(CP, R2, ikb_dup2(4.166664568298827e-2f));
+    CP = ikb_fma2(ikb_mul2(CP, R2), R2, ikb_fma2(R2, ikb_dup2(-0.5f), ikb_dup2(1.0f)));
+    float sp0, sp1, cp0, cp1;
+    ikb_unpack2(SP, sp0, sp1);
+    ikb_unpack2(CP, cp0, cp1);
+    const float ss0 = (q0 & 1) ? cp0 : sp0, cc0 = (q0 & 1) ? sp0 : cp0;
+    const float ss1 = (q1 & 1) ? cp1 : sp1, cc1 = (q1 & 1) ? sp1 : cp1;
+    s0 = (q0 & 2) ? -ss0 : ss0;
+    c0 = ((q0 + 1) & 2) ? -cc0 : cc0;
+    s1 = (q1 & 2) ? -ss1 : ss1;
+    c1 = ((q1 + 1) & 2) ? -cc1 : cc1;
+}
+
 // Closed form for arms whose joints 2..4 have alpha == 0 (see fk_position): the constants are passed as scalars so
 // that the solvers' out-of-line epilogue helpers can call it without the robot block.
 template <typename Real>

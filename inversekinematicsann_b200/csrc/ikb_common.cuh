@@ -26,6 +26,10 @@ struct IkbRobot {
     double seed_xyz[12];  // the theta_1 = 0 chain in 3-D (generic path)
     double seed_ab;       // distance origin -> first joint (|AB| of inverse.py:68)
     double seed_ab2, half_inv_ab;  // |AB|^2 and 1 / (2 |AB|) for the cosine of inverse.py:77-81
+    // the three cosines of inverse.py:77-100 when the segments have their link lengths (any chain after >= 1 pass):
+    // cos_k = (cos_sum[k] - opposite^2) * cos_inv[k], sums |AB|^2 + d1^2, d1^2 + d2^2, d2^2 + d3^2 and
+    // 1 / (2 |AB| d1), 1 / (2 d1 d2), 1 / (2 d2 d3)
+    double cos_sum[3], cos_inv[3];
     double links[4];      // joints_distances
     double limits[6];     // xlo, xhi, ylo, yhi, zlo, zhi
     double tol;

@@ -9,7 +9,8 @@ import conftest as C
 pytestmark = pytest.mark.gpu
 
 TOL_NORTH_STAR = 1e-4   # rad, BASELINE.json
-TOL_F64_MODE = 1e-9     # rad, what the fp64 iterate actually achieves
+TOL_F64_MODE = 1e-9     # rad, what the fp64 iterate actually achieves (float64 angle buffers)
+TOL_F32_BUFFER = 1e-6   # rad, float32 angle buffers: fp64 iterate and cosines, trigonometric tail in fp32
 
 
 @pytest.fixture(scope="module")
@@ -93,7 +94,29 @@ def test_input_forms_and_order(ik, golden_fabrik):
     # fp32 output buffer through the engine API
     out, _ = ik._engine().fabrik_solve(xyz, out_dtype=np.float32)
     assert out.dtype == np.float32
-    np.testing.assert_allclose(out, want, rtol=0, atol=5e-7)
+    np.testing.assert_allclose(out, want, rtol=0, atol=TOL_F32_BUFFER)
+
+
+def test_float32_buffer_tail_bound(ik):
+    """A float32 angle buffer gets the trigonometric tail of the angle extraction (acos / atan2 after the 8-decimal
+    rounding of the cosine, inverse.py:79-108) evaluated on the fp32 pipe; a float64 buffer keeps fp64 throughout.
+    Both against the oracle on a uniform workspace sample (reachable and out-of-reach rows, both pass loops):
+    float32 buffer <= 1e-6 rad (measured 4e-7: two fp32 roundings around pi), float64 buffer <= 1e-9 rad, the
+    iteration counts identical either way."""
+    from oracle import c_oracle
+    rng = np.random.RandomState(77)
+    xyz = rng.rand(200_000, 3) * [6, 12, 9] + [0, -6, -3]
+    want = c_oracle.fabrik_ikine(xyz)
+    ok = np.isfinite(want["angles"]).all(axis=1)
+    eng = ik._engine()
+    out32, st32, it32 = eng.fabrik_solve(xyz, out_dtype=np.float32, return_iters=True)
+    out64, st64, it64 = eng.fabrik_solve(xyz, out_dtype=np.float64, return_iters=True)
+    d32 = np.abs(out32.astype(np.float64) - want["angles"])[ok].max()
+    d64 = np.abs(out64 - want["angles"])[ok].max()
+    print(f"float32 buffer max |dtheta| {d32:.2e}, float64 buffer {d64:.2e}")
+    assert d32 <= TOL_F32_BUFFER and d64 <= TOL_F64_MODE
+    assert np.array_equal(it32, want["iters"]) and np.array_equal(it64, want["iters"])
+    assert st32.sum_iterations == st64.sum_iterations == int(want["iters"].sum())
 
 
 def test_permutation_invariance(ik):
@@ -205,6 +228,20 @@ def test_full_size_properties():
     eng.fabrik_solve_device(xyz, out2)
     torch.cuda.synchronize()
     assert torch.equal(out.view(torch.int32), out2.view(torch.int32))
+    # the full-size launch itself against the oracle: 1e5 rows spread over the whole batch (every 1000th row), angles
+    # within the float32-buffer bound and identical iteration counts
+    from oracle import c_oracle
+    it = torch.empty(n, device="cuda", dtype=torch.int32)
+    eng.fabrik_solve_device(xyz, out2, iters=it)
+    assert torch.equal(out.view(torch.int32), out2.view(torch.int32))      # asking for the counts changes nothing
+    pick = torch.arange(0, n, 1000, device="cuda")
+    sub = xyz[pick].double().cpu().numpy()
+    want = c_oracle.fabrik_ikine(sub)
+    got, got_it = out[pick].double().cpu().numpy(), it[pick].cpu().numpy()
+    ok = np.isfinite(want["angles"]).all(axis=1)
+    assert ok.sum() == len(sub)
+    assert np.array_equal(got_it, want["iters"])
+    assert np.abs(got - want["angles"]).max() <= TOL_F32_BUFFER
 
 
 @pytest.mark.parametrize("tol,max_iter", [(1e-2, 100), (1e-3, 10), (1e-5, 30), (1e-3, 1)])
@@ -315,10 +352,14 @@ def test_non_planar_robot_takes_the_generic_kernel():
         ikg.ikine([[1, 2, 3], [1, 2, 7]])
 
 
-def test_out_of_reach_split_is_value_identical(ik):
-    """Batches >= 65 536 rows run the split kernel (out-of-reach targets in lockstep, csrc/fabrik.cu is_far), smaller
-    ones the lane-refill kernel alone: the same rows must come out identical, in particular in the thin shell
-    around |T - S| = d1 + d2 + d3 + tol where the predicate flips."""
+def test_out_of_reach_split_is_value_identical(ik, tmp_path):
+    """Out-of-reach targets run in lockstep batches of 64, everything else through the lane-refill loop (csrc/fabrik.cu
+    is_far); IKB_FABRIK_SPLIT=0 sends every row through the lane-refill loop.  The same rows must come out bit-identical
+    either way and whatever the batch they arrive in -- in particular in the thin shell around
+    |T - S| = d1 + d2 + d3 + tol where the predicate flips."""
+    import os
+    import subprocess
+    import sys
     rng = np.random.RandomState(77)
     n = 90_000
     xyz = rng.rand(n, 3) * [6, 12, 9] + [0, -6, -3]
@@ -339,6 +380,23 @@ def test_out_of_reach_split_is_value_identical(ik):
     it_pieces = np.concatenate([p[1] for p in parts])
     assert np.array_equal(it_whole, it_pieces)
     assert np.array_equal(whole, pieces, equal_nan=True)
+    # the same rows without the lockstep path, in a fresh process (the switch is read once per process)
+    np.save(tmp_path / "xyz.npy", xyz)
+    code = ("import sys, numpy as np; sys.path.insert(0, sys.argv[1]);"
+            "from inversekinematicsann_b200.kinematics.inverse import FabrikInverseKinematics as F;"
+            "from inversekinematicsann_b200.robot.robot import SixDOFRobot as R;"
+            "ik = F(R.dh_matrix, R.links_lengths, R.effector_workspace_limits);"
+            "a, it = ik.ikine(np.load(sys.argv[2]), as_array=True, return_iterations=True);"
+            "a32 = ik.ikine(np.load(sys.argv[2]), out=np.empty((len(a), 4), np.float32));"
+            "np.savez(sys.argv[3], a=a, it=it, a32=a32)")
+    env = dict(os.environ, IKB_FABRIK_SPLIT="0")
+    subprocess.run([sys.executable, "-c", code, C.ROOT, str(tmp_path / "xyz.npy"), str(tmp_path / "nosplit.npz")],
+                   env=env, check=True, timeout=600)
+    nosplit = np.load(tmp_path / "nosplit.npz")
+    assert np.array_equal(it_whole, nosplit["it"])
+    assert np.array_equal(whole, nosplit["a"], equal_nan=True)
+    whole32 = ik.ikine(xyz, out=np.empty((n, 4), np.float32))
+    assert np.array_equal(whole32, nosplit["a32"], equal_nan=True)
     far = np.linalg.norm(xyz - [0, 0, 2], axis=1) > 6.0011
     assert (it_whole[far] == 100).all() and far.sum() > 20_000
     from oracle import c_oracle

@@ -96,8 +96,10 @@ def test_fabrik_fused_fk_error_equals_k3(dtype, n):
     tol = 2e-6 if dtype == np.float32 else 1e-12
     assert np.abs(fused - separate).max() <= tol
     assert abs(ik.last_stats.mean_fk_error - float(np.mean(separate, dtype=np.float64))) <= 1e-6
-    # the same angles as without the fused error
-    assert np.array_equal(angles, ik.ikine(pts, as_array=True).astype(dtype))
+    # the same angles as without the fused error (same buffer precision: a float32 buffer gets the fp32
+    # trigonometric tail, see csrc/fabrik.cu acos_f32), and within the float32-buffer bound of the fp64 result
+    assert np.array_equal(angles, ik.ikine(pts, out=np.empty_like(out)), equal_nan=True)
+    assert np.nanmax(np.abs(angles - ik.ikine(pts, as_array=True))) <= (1e-6 if dtype == np.float32 else 0.0)
 
 
 def test_fabrik_fused_fk_error_vs_oracle():
