@@ -535,8 +535,7 @@ def main():
         with threadpool_limits(limits=os.cpu_count() or 1):
             p32 = np_oracle.mlp_predict(p_pts, W, b, *sc, dtype=np.float32)
             p64 = np_oracle.mlp_predict(p_pts, W, b, *sc, dtype=np.float64)
-        torch.set_num_threads(os.cpu_count() or 1)
-        pt32 = torch_oracle.mlp_predict(p_pts, W, b, *sc)
+        pt32 = torch_oracle.mlp_predict_fresh_process(p_pts, W, b, *sc)
         d32 = np.abs(p_got.astype(np.float64) - p32).max(axis=1)
         _, _, fk_ref = c_oracle.fk_positions(p32.astype(np.float64), targets=p_pts)
         _, _, fk_eng = c_oracle.fk_positions(p_got.astype(np.float64), targets=p_pts)

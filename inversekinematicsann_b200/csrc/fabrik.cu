@@ -26,6 +26,22 @@
 
 #include "fk_device.cuh"
 
+// -DIKB_FABRIK_CHECK: trap when a shared-memory queue would be indexed outside its capacity (the pool's
+// compute-sanitizer is closed, so the debug variant of tools/build_variant.sh carries its own bounds checks)
+#ifdef IKB_FABRIK_CHECK
+#include <cstdio>
+#define IKB_CHECK(cond)                                                                    \
+    do {                                                                                   \
+        if (!(cond)) {                                                                     \
+            printf("IKB_CHECK failed: %s (line %d, block %d thread %d)\n", #cond, __LINE__, \
+                   (int)blockIdx.x, (int)threadIdx.x);                                     \
+            __trap();                                                                      \
+        }                                                                                  \
+    } while (0)
+#else
+#define IKB_CHECK(cond) do {} while (0)
+#endif
+
 #define IKB_FABRIK_CHUNK 256
 #define IKB_FABRIK_WARPS 8
 #define IKB_Q 64  // per-warp input queue capacity (ring), power of two
@@ -574,6 +590,7 @@ __device__ __forceinline__ void fabrik_warp_loop(const FabrikArgs &a, WarpQueues
         }
         in_cnt += __popc(keep_n);
         far_cnt += __popc(keep_f);
+        IKB_CHECK(in_cnt <= IKB_Q && far_cnt <= IKB_FAR_Q && in_cnt >= 0 && far_cnt >= 0);
         __syncwarp();
     };
 
@@ -581,6 +598,7 @@ __device__ __forceinline__ void fabrik_warp_loop(const FabrikArgs &a, WarpQueues
     auto drain = [&](bool final) {
         while (out_cnt >= 32 || (final && out_cnt > 0)) {
             const int n_take = min(32, out_cnt);
+            IKB_CHECK(out_cnt > 0 && out_cnt <= IKB_OUT_Q);
             if (lane < n_take) {
                 const int slot = (out_head + lane) & (IKB_OUT_Q - 1);
                 const int k_raw = q.out_k[slot];
@@ -602,6 +620,7 @@ __device__ __forceinline__ void fabrik_warp_loop(const FabrikArgs &a, WarpQueues
     // slots run on a harmless dummy target
     auto far_batch = [&]() {
         const int nb = min(far_cnt, IKB_FAR_BATCH);
+        IKB_CHECK(nb > 0 && out_cnt < 32);
         PlanarChain<Real> fc[2];
         Real fTr[2], fTz[2];
 #pragma unroll
@@ -635,6 +654,7 @@ __device__ __forceinline__ void fabrik_warp_loop(const FabrikArgs &a, WarpQueues
                 q.out_th1[slot] = q.far_th1[e];
             }
             out_cnt += cnt_u;
+            IKB_CHECK(out_cnt <= IKB_OUT_Q);
             __syncwarp();
             drain(false);
         }
@@ -721,6 +741,7 @@ __device__ __forceinline__ void fabrik_warp_loop(const FabrikArgs &a, WarpQueues
                             active = false;
                     }
                     out_cnt += nf;
+                    IKB_CHECK(out_cnt <= IKB_OUT_Q && in_cnt >= 0);
                     if (nf > in_cnt) {  // warp-uniform: some lanes found the queue empty
                         in_head = (in_head + in_cnt) & (IKB_Q - 1);
                         in_cnt = 0;

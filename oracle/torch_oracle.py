@@ -57,3 +57,33 @@ def mlp_predict(xyz, weights, biases, mean_x, scale_x, mean_y, scale_y, chunk=65
             y.mul_(sy).add_(my)                                                         # inverse_transform, in place
             out[lo:lo + chunk] = y.numpy()
     return out
+
+
+def mlp_predict_fresh_process(xyz, weights, biases, mean_x, scale_x, mean_y, scale_y, timeout=900):
+    """mlp_predict in a new interpreter.  In a long-lived process that has already loaded CUDA, OpenMP code of its own
+    and several BLAS users, torch's CPU GEMMs were seen to come out 5e-4 rad off on one B200 host while the very same
+    call in a fresh process agreed with NumPy to 1.5e-6 (gpurun_out diagnostics, round 2); a checker must not depend on
+    that, so the tests and bench.py run it out of process."""
+    import os
+    import subprocess
+    import sys
+    import tempfile
+    with tempfile.TemporaryDirectory() as tmp:
+        arrays = {"xyz": np.asarray(xyz), "mean_x": np.asarray(mean_x), "scale_x": np.asarray(scale_x),
+                  "mean_y": np.asarray(mean_y), "scale_y": np.asarray(scale_y), "n_layers": np.array(len(weights))}
+        for i, (w, b) in enumerate(zip(weights, biases)):
+            arrays[f"W{i}"], arrays[f"b{i}"] = np.asarray(w), np.asarray(b)
+        src, dst = os.path.join(tmp, "in.npz"), os.path.join(tmp, "out.npy")
+        np.savez(src, **arrays)
+        env = dict(os.environ, CUDA_VISIBLE_DEVICES="")
+        subprocess.run([sys.executable, os.path.abspath(__file__), src, dst], check=True, timeout=timeout, env=env)
+        return np.load(dst)
+
+
+if __name__ == "__main__":
+    import sys
+    data = np.load(sys.argv[1])
+    nl = int(data["n_layers"])
+    out = mlp_predict(data["xyz"], [data[f"W{i}"] for i in range(nl)], [data[f"b{i}"] for i in range(nl)],
+                      data["mean_x"], data["scale_x"], data["mean_y"], data["scale_y"])
+    np.save(sys.argv[2], out)

@@ -163,7 +163,7 @@ def test_default_mode_against_independent_torch_fp32():
     xyz = _points(30_000, seed=23).astype(np.float32)
     got = ann.ikine(xyz, as_array=True)
     sc = (a.x_data_skaler.mean_, a.x_data_skaler.scale_, a.y_data_skaler.mean_, a.y_data_skaler.scale_)
-    t32 = torch_oracle.mlp_predict(xyz, a.model.kernels, a.model.biases, *sc)
+    t32 = torch_oracle.mlp_predict_fresh_process(xyz, a.model.kernels, a.model.biases, *sc)
     n32 = np_oracle.mlp_predict(xyz, a.model.kernels, a.model.biases, *sc)
     d_t, d_n, d_cpu = np.abs(got - t32).max(axis=1), np.abs(got - n32).max(axis=1), np.abs(t32 - n32).max(axis=1)
     print(f"kernel vs torch fp32 max {d_t.max():.2e}, vs numpy fp32 max {d_n.max():.2e}, torch vs numpy max {d_cpu.max():.2e}")

@@ -1,5 +1,5 @@
-set -x
 mkdir -p gpurun_out
-python -m pytest tests -m gpu -q > gpurun_out/r02g_pytest.log 2>&1; echo "pytest rc=$?"
-tail -8 gpurun_out/r02g_pytest.log
-python tools/time_kernels.py --only k1w,k1r,k3 > gpurun_out/r02g_time.json 2> gpurun_out/r02g_time.err; cat gpurun_out/r02g_time.json
+for v in default k3_minb3 k3_minb5 k3_minb6; do
+  if [ $v = default ]; then python tools/time_kernels.py --only k1w,k3 --reps 10 2>/dev/null | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('$v', d['k3'])";
+  else IKB200_LIB=gpurun_variants/$v.so python tools/time_kernels.py --only k1w,k3 --reps 10 2>/dev/null | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('$v', d['k3'])"; fi
+done 2>&1 | tee gpurun_out/r02k_k3_variants.log
