@@ -421,9 +421,11 @@ def main():
         n_total = n * world
         full = torch.empty(n_total, 4, device=dev, dtype=torch.float32) if rank == 0 else None
         g_steps = max(2, min(args.steps, 5))
+        GATHER_CHUNK = 1 << 24   # rows per K1 launch when chunks are shipped while the next one is solved
         only_secs, _, _ = timed_device_loop(lambda: gather_rows(angles, n_total, dst=0, out=full), g_steps, 2)
         both_secs, _, _ = timed_device_loop(
-            lambda: sh.ikine_device(xyz, angles, n_total=n_total, gather_dst=0, gather_out=full, check=False), g_steps, 2)
+            lambda: sh.ikine_device(xyz, angles, n_total=n_total, gather_dst=0, gather_out=full, check=False,
+                                    chunk_rows=GATHER_CHUNK), g_steps, 2)
         # every shard must have landed at its own rows of rank 0's buffer
         probe = torch.zeros(world, dtype=torch.float64, device=dev)
         probe[rank] = angles[:4096].double().sum() + angles[-4096:].double().sum()
@@ -439,9 +441,11 @@ def main():
                   "solve_ms": secs / args.steps * 1e3, "overlapped_ms": both_secs / g_steps * 1e3,
                   "solve_plus_gather_over_solve": (both_secs / g_steps) / (secs / args.steps),
                   "order_verified": order_ok,
-                  "how": "ShardedFabrik.ikine_device: K1 per 4 Mi-row chunk, finished chunks shipped to rank 0 with NCCL "
+                  "chunk_rows": GATHER_CHUNK,
+                  "how": "ShardedFabrik.ikine_device: K1 per 16 Mi-row chunk, finished chunks shipped to rank 0 with NCCL "
                          "send/recv (point-to-point, received in place) while the next chunk is solved; `ms` is the "
-                         "same gather after the solve, not overlapped"}
+                         "same gather after the solve, not overlapped.  All other ranks' rows converge on ONE GPU, so "
+                         "the gather is bound by that GPU's NVLink ingest: (N-1) x 1.6 GB at GBps_into_dst"}
         del full
 
     # ---- FABRIK end to end: host buffers through the public ikine() call --------------------------

@@ -132,7 +132,7 @@ class _ShardedIkine:
         return None if full is None else full.cpu().numpy()
 
     def ikine_device(self, xyz_shard, out_shard=None, n_total=None, gather_dst=None, gather_out=None,
-                     chunk_rows=1 << 22, fk_error=False, check=True):
+                     chunk_rows=1 << 24, fk_error=False, check=True):
         """Solve this rank's rows where they are.  xyz_shard: (n_local, 3) CUDA tensor = rows
         shard_range(n_total, rank, world) of the trajectory; out_shard: optional (n_local, 4) CUDA tensor.
         Returns out_shard, or -- with gather_dst -- the full (n_total, 4) tensor on that rank and None elsewhere.
@@ -189,6 +189,41 @@ class _ShardedIkine:
         return out_shard
 
 
+    def ikine_from_root(self, points=None, root=0, out=None):
+        """One request that arrives on ONE rank (the broker of rpc_broker.py:76-100), served by all GPUs: `root` pushes
+        the (n, 3) host array to its GPU, the shards travel to their GPUs over NCCL send/recv, every rank solves its
+        rows in HBM, the angles are gathered back to `root` and copied into `out` (e.g. a pinned reply buffer).  Every
+        rank calls this; `points` / `out` are only read on `root`.  Returns the (n, 4) host array on `root`.
+        The request crosses PCIe once, on `root`'s link: that link, not the solve, bounds this path."""
+        import numpy as np
+        world, rank = self._world_rank()
+        eng = self._engine()
+        dev = torch.device("cuda", eng.device) if (world == 1 or dist.get_backend() == "nccl") else torch.device("cpu")
+        meta = [None]
+        if rank == root:
+            from .kinematics._shared import points_to_array
+            arr = points_to_array(points)
+            meta = [(arr.shape[0], str(arr.dtype))]
+        if world > 1:
+            dist.broadcast_object_list(meta, src=root)
+        n_total, dtype_name = meta[0]
+        tdtype = torch.float32 if dtype_name == "float32" else torch.float64
+        full_in = None
+        if rank == root:
+            import warnings
+            with warnings.catch_warnings():  # a request body decoded in place is a read-only view: it is only read
+                warnings.simplefilter("ignore", UserWarning)
+                full_in = torch.from_numpy(arr).to(dev, non_blocking=True)
+        shard = scatter_rows(full_in, n_total, 3, tdtype, dev, src=root)
+        full = self.ikine_device(shard, n_total=n_total, gather_dst=root if world > 1 else None)
+        if rank != root:
+            return None
+        if out is None:
+            out = np.empty((n_total, 4), dtype=np.dtype(str(full.dtype).replace("torch.", "")))
+        torch.from_numpy(out).copy_(full)      # device -> host (pinned `out`: one DMA)
+        return out
+
+
 def scatter_rows(full_rows, n_total, cols, dtype, device, src=0):
     """The inverse of gather_rows: rank `src` holds (n_total, cols) rows on its device, every rank gets its
     contiguous shard (point-to-point sends of unequal shards; `full_rows` is None elsewhere)."""
@@ -221,36 +256,6 @@ class _RowPrinter:
         if 0 <= j < self.shard.shape[0]:
             return self.shard[j].tolist()
         return f"#{i}"
-
-
-    def ikine_from_root(self, points=None, root=0, out=None):
-        """One request that arrives on ONE rank (the broker of rpc_broker.py:76-100), served by all GPUs: `root` pushes
-        the (n, 3) host array to its GPU, the shards travel to their GPUs over NCCL send/recv, every rank solves its
-        rows in HBM, the angles are gathered back to `root` and copied into `out` (e.g. a pinned reply buffer).  Every
-        rank calls this; `points` / `out` are only read on `root`.  Returns the (n, 4) host array on `root`.
-        The request crosses PCIe once, on `root`'s link: that link, not the solve, bounds this path."""
-        import numpy as np
-        world, rank = self._world_rank()
-        eng = self._engine()
-        dev = torch.device("cuda", eng.device) if (world == 1 or dist.get_backend() == "nccl") else torch.device("cpu")
-        meta = [None]
-        if rank == root:
-            from .kinematics._shared import points_to_array
-            arr = points_to_array(points)
-            meta = [(arr.shape[0], str(arr.dtype))]
-        if world > 1:
-            dist.broadcast_object_list(meta, src=root)
-        n_total, dtype_name = meta[0]
-        tdtype = torch.float32 if dtype_name == "float32" else torch.float64
-        full_in = torch.from_numpy(arr).to(dev, non_blocking=True) if rank == root else None
-        shard = scatter_rows(full_in, n_total, 3, tdtype, dev, src=root)
-        full = self.ikine_device(shard, n_total=n_total, gather_dst=root if world > 1 else None)
-        if rank != root:
-            return None
-        if out is None:
-            out = np.empty((n_total, 4), dtype=np.dtype(str(full.dtype).replace("torch.", "")))
-        torch.from_numpy(out).copy_(full)      # device -> host (pinned `out`: one DMA)
-        return out
 
 
 class ShardedFabrik(_ShardedIkine):

@@ -123,6 +123,12 @@ def _device_worker(rank, world, port, n_total, chunk_rows, dst, out_dir):
     assert local_only.shape == (hi - lo, 4)
     if rank == dst:
         np.save(os.path.join(out_dir, "full.npy"), full.numpy())
+    # one request that arrives on ONE rank, served by all: scatter -> solve -> gather -> host array on the root
+    pts = np.arange(n_total, dtype=np.float64)[:, None].repeat(3, axis=1) if rank == dst else None
+    served = sh.ikine_from_root(pts, root=dst)
+    assert (served is not None) == (rank == dst)
+    if rank == dst:
+        np.testing.assert_array_equal(served, np.arange(n_total)[:, None] * np.array([1.0, 2.0, 3.0, 4.0]))
     lo_last = shard_range(n_total, world - 1, world)[0]
     assert sh.ik.last_stats.n_solved == n_total and sh.ik.last_stats.first_out_of_limits == lo_last + 2
     row, printed = FakeIk.raised

@@ -1,5 +1,3 @@
 mkdir -p gpurun_out
-for v in default k3_minb3 k3_minb5 k3_minb6; do
-  if [ $v = default ]; then python tools/time_kernels.py --only k1w,k3 --reps 10 2>/dev/null | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('$v', d['k3'])";
-  else IKB200_LIB=gpurun_variants/$v.so python tools/time_kernels.py --only k1w,k3 --reps 10 2>/dev/null | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('$v', d['k3'])"; fi
-done 2>&1 | tee gpurun_out/r02k_k3_variants.log
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 5 --warmup 3 > gpurun_out/r02l_bench_n2.json 2> gpurun_out/r02l_bench_n2.err; echo "bench n2 rc=$?"; tail -5 gpurun_out/r02l_bench_n2.err
+python -m pytest tests/test_gpu_sharded.py -q > gpurun_out/r02l_pytest_sharded.log 2>&1; tail -3 gpurun_out/r02l_pytest_sharded.log
