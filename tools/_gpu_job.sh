@@ -1,3 +1,3 @@
 mkdir -p gpurun_out
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 5 --warmup 3 > gpurun_out/r02l_bench_n2.json 2> gpurun_out/r02l_bench_n2.err; echo "bench n2 rc=$?"; tail -5 gpurun_out/r02l_bench_n2.err
-python -m pytest tests/test_gpu_sharded.py -q > gpurun_out/r02l_pytest_sharded.log 2>&1; tail -3 gpurun_out/r02l_pytest_sharded.log
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 8 --steps 5 --warmup 3 > gpurun_out/r02m_bench_n8.json 2> gpurun_out/r02m_bench_n8.err; echo "bench n8 rc=$?"; tail -3 gpurun_out/r02m_bench_n8.err
+nvidia-smi topo -m > gpurun_out/r02m_topo.txt 2>&1; lscpu | head -25 > gpurun_out/r02m_lscpu.txt; numactl -H >> gpurun_out/r02m_lscpu.txt 2>&1
