@@ -488,15 +488,26 @@ __device__ __forceinline__ void fabrik_epilogue(const FabrikArgs &a, int idx, in
 #define IKB_OUT_Q 64
 #define IKB_FAR_BATCH 64
 #define IKB_FAR_Q (IKB_FAR_BATCH + 32)
+// Records are kept as pairs (16-byte shared-memory accesses for fp64): the lane-refill loop is bound by instruction
+// issue on short-iteration data, and a park-and-refill step moves 13 values per finished chain.
+template <typename Real>
+struct Pair;
+template <>
+struct Pair<double> {
+    using type = double2;
+};
+template <>
+struct Pair<float> {
+    using type = float2;
+};
 template <typename Real, typename Th1>
 struct WarpQueues {
-    Real in_tr[IKB_Q], in_tz[IKB_Q];
-    Real out_c[6][IKB_OUT_Q];  // r1, z1, r2, z2, Tr, Tz
-    Real far_tr[IKB_FAR_Q], far_tz[IKB_FAR_Q];
+    using Real2 = typename Pair<Real>::type;
+    Real2 in_t[IKB_Q];                                           // (Tr, Tz)
+    Real2 out_j1[IKB_OUT_Q], out_j2[IKB_OUT_Q], out_t[IKB_OUT_Q];  // (r1, z1), (r2, z2), (Tr, Tz)
+    Real2 far_t[IKB_FAR_Q];
+    int2 in_ik[IKB_Q], out_ik[IKB_OUT_Q], far_ik[IKB_FAR_Q];     // (row, iteration count + flags)
     Th1 in_th1[IKB_Q], out_th1[IKB_OUT_Q], far_th1[IKB_FAR_Q];
-    int in_idx[IKB_Q], in_k0[IKB_Q];
-    int out_idx[IKB_OUT_Q], out_k[IKB_OUT_Q];
-    int far_idx[IKB_FAR_Q], far_k0[IKB_FAR_Q];
 };
 
 // One warp's whole job: ONE scan of the input through a global chunk counter; every staged target is classified
@@ -512,6 +523,7 @@ template <typename Real, bool FUSE_FK, bool OUT32>
 __device__ __forceinline__ void fabrik_warp_loop(const FabrikArgs &a, WarpQueues<Real, typename TailType<OUT32>::type> *s_queues)
 {
     using Th1 = typename TailType<OUT32>::type;
+    using Real2 = typename Pair<Real>::type;
     const int lane = threadIdx.x & 31;
     WarpQueues<Real, Th1> &q = s_queues[threadIdx.x >> 5];
     const unsigned lt = ikb_lanemask_lt();
@@ -580,13 +592,15 @@ __device__ __forceinline__ void fabrik_warp_loop(const FabrikArgs &a, WarpQueues
         const unsigned keep_n = __ballot_sync(IKB_FULL_MASK, near), keep_f = __ballot_sync(IKB_FULL_MASK, far);
         if (near) {
             const int slot = (in_head + in_cnt + __popc(keep_n & lt)) & (IKB_Q - 1);
-            q.in_idx[slot] = (int)pf_row; q.in_k0[slot] = k0;
-            q.in_tr[slot] = tr; q.in_tz[slot] = (Real)pz; q.in_th1[slot] = t1;
+            q.in_ik[slot] = make_int2((int)pf_row, k0);
+            q.in_t[slot] = Real2{tr, (Real)pz};
+            q.in_th1[slot] = t1;
         }
         if (far) {
             const int slot = far_cnt + __popc(keep_f & lt);
-            q.far_idx[slot] = (int)pf_row; q.far_k0[slot] = k0;
-            q.far_tr[slot] = tr; q.far_tz[slot] = (Real)pz; q.far_th1[slot] = t1;
+            q.far_ik[slot] = make_int2((int)pf_row, k0);
+            q.far_t[slot] = Real2{tr, (Real)pz};
+            q.far_th1[slot] = t1;
         }
         in_cnt += __popc(keep_n);
         far_cnt += __popc(keep_f);
@@ -601,11 +615,12 @@ __device__ __forceinline__ void fabrik_warp_loop(const FabrikArgs &a, WarpQueues
             IKB_CHECK(out_cnt > 0 && out_cnt <= IKB_OUT_Q);
             if (lane < n_take) {
                 const int slot = (out_head + lane) & (IKB_OUT_Q - 1);
-                const int k_raw = q.out_k[slot];
-                fabrik_epilogue<FUSE_FK, OUT32, sizeof(Real) == 8, Th1>(a, q.out_idx[slot], k_raw, (double)q.out_c[0][slot],
-                                                     (double)q.out_c[1][slot], (double)q.out_c[2][slot],
-                                                     (double)q.out_c[3][slot], (double)q.out_c[4][slot],
-                                                     (double)q.out_c[5][slot], q.out_th1[slot], fk_sum, fk_cnt);
+                const int2 ik = q.out_ik[slot];
+                const int k_raw = ik.y;
+                const Real2 j1 = q.out_j1[slot], j2 = q.out_j2[slot], tt = q.out_t[slot];
+                fabrik_epilogue<FUSE_FK, OUT32, sizeof(Real) == 8, Th1>(a, ik.x, k_raw, (double)j1.x, (double)j1.y,
+                                                                        (double)j2.x, (double)j2.y, (double)tt.x,
+                                                                        (double)tt.y, q.out_th1[slot], fk_sum, fk_cnt);
                 iters_local += (unsigned)(k_raw & IKB_K_MASK);
                 ++solved_local;
                 capped_local += (k_raw & IKB_CAPPED_BIT) ? 1u : 0u;
@@ -626,8 +641,9 @@ __device__ __forceinline__ void fabrik_warp_loop(const FabrikArgs &a, WarpQueues
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
             const int e = u * 32 + lane;
-            fTr[u] = e < nb ? q.far_tr[e] : (Real)100;
-            fTz[u] = e < nb ? q.far_tz[e] : (Real)100;
+            const Real2 ft = q.far_t[e < nb ? e : 0];
+            fTr[u] = e < nb ? ft.x : (Real)100;
+            fTz[u] = e < nb ? ft.y : (Real)100;
             fc[u].r1 = (Real)rc.seed_r[1]; fc[u].z1 = (Real)rc.seed_z[1];
             fc[u].r2 = (Real)rc.seed_r[2]; fc[u].z2 = (Real)rc.seed_z[2];
         }
@@ -646,11 +662,11 @@ __device__ __forceinline__ void fabrik_warp_loop(const FabrikArgs &a, WarpQueues
             if (lane < cnt_u) {
                 const int e = u * 32 + lane;
                 const int slot = (out_head + out_cnt + lane) & (IKB_OUT_Q - 1);
-                q.out_idx[slot] = q.far_idx[e];
-                q.out_k[slot] = max_iter | IKB_CAPPED_BIT | q.far_k0[e];
-                q.out_c[0][slot] = fc[u].r1; q.out_c[1][slot] = fc[u].z1;
-                q.out_c[2][slot] = fc[u].r2; q.out_c[3][slot] = fc[u].z2;
-                q.out_c[4][slot] = fTr[u]; q.out_c[5][slot] = fTz[u];
+                const int2 fik = q.far_ik[e];
+                q.out_ik[slot] = make_int2(fik.x, max_iter | IKB_CAPPED_BIT | fik.y);
+                q.out_j1[slot] = Real2{fc[u].r1, fc[u].z1};
+                q.out_j2[slot] = Real2{fc[u].r2, fc[u].z2};
+                q.out_t[slot] = Real2{fTr[u], fTz[u]};
                 q.out_th1[slot] = q.far_th1[e];
             }
             out_cnt += cnt_u;
@@ -660,27 +676,27 @@ __device__ __forceinline__ void fabrik_warp_loop(const FabrikArgs &a, WarpQueues
         }
         // move the rest (< 32 entries) to the front
         const int rest = far_cnt - nb;
-        int m_idx = 0, m_k0 = 0;
-        Real m_tr = 0, m_tz = 0;
+        int2 m_ik = make_int2(0, 0);
+        Real2 m_t{0, 0};
         Th1 m_th1 = 0;
         if (lane < rest) {
-            m_idx = q.far_idx[nb + lane]; m_k0 = q.far_k0[nb + lane];
-            m_tr = q.far_tr[nb + lane]; m_tz = q.far_tz[nb + lane]; m_th1 = q.far_th1[nb + lane];
+            m_ik = q.far_ik[nb + lane]; m_t = q.far_t[nb + lane]; m_th1 = q.far_th1[nb + lane];
         }
         __syncwarp();
         if (lane < rest) {
-            q.far_idx[lane] = m_idx; q.far_k0[lane] = m_k0;
-            q.far_tr[lane] = m_tr; q.far_tz[lane] = m_tz; q.far_th1[lane] = m_th1;
+            q.far_ik[lane] = m_ik; q.far_t[lane] = m_t; q.far_th1[lane] = m_th1;
         }
         __syncwarp();
         far_cnt = rest;
     };
 
     auto take_target = [&](int slot) {
-        idx = q.in_idx[slot];
-        k = q.in_k0[slot];
-        Tr = q.in_tr[slot];
-        Tz = q.in_tz[slot];
+        const int2 ik = q.in_ik[slot];
+        const Real2 t = q.in_t[slot];
+        idx = ik.x;
+        k = ik.y;
+        Tr = t.x;
+        Tz = t.y;
         th1 = q.in_th1[slot];
         c.r1 = (Real)rc.seed_r[1]; c.z1 = (Real)rc.seed_z[1];
         c.r2 = (Real)rc.seed_r[2]; c.z2 = (Real)rc.seed_z[2];
@@ -717,6 +733,7 @@ __device__ __forceinline__ void fabrik_warp_loop(const FabrikArgs &a, WarpQueues
         //    parked chains is ready, when the staged targets run low while there is input left, or when no lane is live.
         if (active_mask != 0) {
             bool leave = false;
+            const bool more_input = pf_m > 0;
             do {
                 bool more = false;
                 if (!zero_iter) {
@@ -729,11 +746,10 @@ __device__ __forceinline__ void fabrik_warp_loop(const FabrikArgs &a, WarpQueues
                     const int rank = __popc(m & lt), nf = __popc(m);
                     if (fin) {
                         const int slot = (out_head + out_cnt + rank) & (IKB_OUT_Q - 1);
-                        q.out_idx[slot] = idx;
-                        q.out_k[slot] = more ? (k | IKB_CAPPED_BIT) : k;
-                        q.out_c[0][slot] = c.r1; q.out_c[1][slot] = c.z1;
-                        q.out_c[2][slot] = c.r2; q.out_c[3][slot] = c.z2;
-                        q.out_c[4][slot] = Tr; q.out_c[5][slot] = Tz;
+                        q.out_ik[slot] = make_int2(idx, more ? (k | IKB_CAPPED_BIT) : k);
+                        q.out_j1[slot] = Real2{c.r1, c.z1};
+                        q.out_j2[slot] = Real2{c.r2, c.z2};
+                        q.out_t[slot] = Real2{Tr, Tz};
                         q.out_th1[slot] = th1;
                         if (rank < in_cnt)
                             take_target((in_head + rank) & (IKB_Q - 1));
@@ -742,15 +758,16 @@ __device__ __forceinline__ void fabrik_warp_loop(const FabrikArgs &a, WarpQueues
                     }
                     out_cnt += nf;
                     IKB_CHECK(out_cnt <= IKB_OUT_Q && in_cnt >= 0);
-                    if (nf > in_cnt) {  // warp-uniform: some lanes found the queue empty
+                    if (nf <= in_cnt) {  // every finished lane found a staged target: the loop stays at full width
+                        in_head = (in_head + nf) & (IKB_Q - 1);
+                        in_cnt -= nf;
+                        leave = (out_cnt >= 32) | (more_input & (in_cnt < IKB_FABRIK_LOW_WATER));
+                    } else {             // the queue ran dry: leave, restage (or carry on with fewer lanes in the tail)
                         in_head = (in_head + in_cnt) & (IKB_Q - 1);
                         in_cnt = 0;
                         active_mask = __ballot_sync(IKB_FULL_MASK, active);
-                    } else {
-                        in_head = (in_head + nf) & (IKB_Q - 1);
-                        in_cnt -= nf;
+                        leave = true;
                     }
-                    leave = (out_cnt >= 32) | (active_mask == 0) | ((pf_m > 0) & (in_cnt < IKB_FABRIK_LOW_WATER));
                 }
             } while (!leave);
             __syncwarp();

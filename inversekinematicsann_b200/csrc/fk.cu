@@ -7,6 +7,8 @@
 // (cli.py:60, inverse.py:130, tests/forward_unit.py:30) and ||pos - target||.  The chain kernel
 // returns all four cumulative 4x4 matrices for the (T, [T1..T4]) return value of fkine.
 // HBM-bound: 16 B angles + 12 B target in, 4 B error out per row (fp32 buffers).
+#include <cstdlib>
+
 #include "fk_device.cuh"
 
 namespace {
@@ -128,7 +130,7 @@ __global__ void __launch_bounds__(256, FK_MINB) fk_kernel(const FkArgs a)
 // (ikb_sincos2: bit-identical to the scalar code, about half its instructions).  The chain arithmetic is the same inline
 // function as everywhere else, so the errors are the ones the generic kernel and the solvers' fused epilogues produce.
 #ifndef FK_PAIR_MINB
-#define FK_PAIR_MINB 4
+#define FK_PAIR_MINB 3  // 80 registers: room for the software-pipelined loads without spills (4 CTAs: 64 registers, spills)
 #endif
 __global__ void __launch_bounds__(256, FK_PAIR_MINB) fk_error_pairs_kernel(const FkArgs a)
 {
@@ -145,13 +147,37 @@ __global__ void __launch_bounds__(256, FK_PAIR_MINB) fk_error_pairs_kernel(const
         float px, py, pz;
         fk_planar_tail_position<float>(s, c, k[0], k[1], k[2], k[3], k[4], k[5], k[6], k[7], px, py, pz);
         const float dx = px - tx, dy = py - ty, dz = pz - tz;
-        const float err = sqrt(dx * dx + dy * dy + dz * dz);
+        // sqrt.approx (one MUFU, 1 ulp) instead of the IEEE root with its fix-up branch: the error is a diagnostic
+        // in metres, and the kernel is bound by instruction issue
+        float err;
+        asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(err) : "f"(dx * dx + dy * dy + dz * dz));
         const bool ok = !(fabsf(th.x) > TWO_PI) & !(fabsf(th.y) > TWO_PI) & !(fabsf(th.z) > TWO_PI) & !(fabsf(th.w) > TWO_PI);
         return ok ? err : __int_as_float(0x7fc00000);
     };
-    for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < n_pairs; p += stride) {
-        const float4 th0 = __ldg(ang + 2 * p), th1 = __ldg(ang + 2 * p + 1);
-        const float2 t0 = __ldg(tgt + 3 * p), t1 = __ldg(tgt + 3 * p + 1), t2 = __ldg(tgt + 3 * p + 2);
+#ifndef FK_PAIR_PREFETCH
+#define FK_PAIR_PREFETCH 1
+#endif
+    long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    float4 n_th0, n_th1;
+    float2 n_t0, n_t1, n_t2;
+    if (FK_PAIR_PREFETCH && p < n_pairs) {  // software pipeline: the next trip's loads are in flight during this trip's arithmetic
+        n_th0 = __ldg(ang + 2 * p); n_th1 = __ldg(ang + 2 * p + 1);
+        n_t0 = __ldg(tgt + 3 * p); n_t1 = __ldg(tgt + 3 * p + 1); n_t2 = __ldg(tgt + 3 * p + 2);
+    }
+    for (; p < n_pairs; p += stride) {
+        float4 th0, th1;
+        float2 t0, t1, t2;
+        if (FK_PAIR_PREFETCH) {
+            th0 = n_th0; th1 = n_th1; t0 = n_t0; t1 = n_t1; t2 = n_t2;
+            const long long pn = p + stride;
+            if (pn < n_pairs) {
+                n_th0 = __ldg(ang + 2 * pn); n_th1 = __ldg(ang + 2 * pn + 1);
+                n_t0 = __ldg(tgt + 3 * pn); n_t1 = __ldg(tgt + 3 * pn + 1); n_t2 = __ldg(tgt + 3 * pn + 2);
+            }
+        } else {
+            th0 = __ldg(ang + 2 * p); th1 = __ldg(ang + 2 * p + 1);
+            t0 = __ldg(tgt + 3 * p); t1 = __ldg(tgt + 3 * p + 1); t2 = __ldg(tgt + 3 * p + 2);
+        }
         float s0[4], c0[4], s1[4], c1[4];
         ikb_sincos2(th0.x, th1.x, s0[0], c0[0], s1[0], c1[0]);
         ikb_sincos2(th0.y, th1.y, s0[1], c0[1], s1[1], c1[1]);
@@ -188,6 +214,106 @@ __global__ void __launch_bounds__(256, FK_PAIR_MINB) fk_error_pairs_kernel(const
     err_sum = ikb_warp_sum(err_sum);
     err_cnt = ikb_warp_sum(err_cnt);
     if ((threadIdx.x & 31) == 0 && err_cnt) {
+        atomicAdd(&a.stats->sum_fk_error, err_sum);
+        atomicAdd(&a.stats->n_fk_error, (unsigned long long)err_cnt);
+    }
+}
+
+// ---- the same rows through an asynchronous-copy ring -------------------------------------------------------------------
+// With the instruction count down, what keeps the pair kernel at ~0.8 of the HBM roofline is bytes in flight: a thread
+// holds its next loads in registers (56 B) and 24 warps per SM make 43 KB.  Here a WARP owns 32 consecutive pairs per
+// trip (1 KB of angles + 768 B of targets, both contiguous) and streams them global -> shared with cp.async through a
+// ring of FK_STREAM_STAGES trips, no registers involved: up to 3.5 KB per warp in flight, 32 warps per SM.  Arithmetic
+// and results are those of fk_error_pairs_kernel.  Needs 16-byte aligned buffers; the last partial trip goes to the
+// pair kernel.
+#ifndef FK_STREAM_STAGES
+#define FK_STREAM_STAGES 3
+#endif
+#define FK_STREAM_WARPS 8
+struct FkStage {
+    float4 ang[64];   // 32 pairs x 2 rows
+    float2 tgt[96];   // 32 pairs x 6 floats
+};
+
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem)
+                 : "memory");
+}
+
+__global__ void __launch_bounds__(FK_STREAM_WARPS * 32, 4) fk_error_stream_kernel(const FkArgs a, long long n_trips)
+{
+    __shared__ __align__(16) FkStage s_ring[FK_STREAM_WARPS][FK_STREAM_STAGES];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    FkStage *ring = s_ring[warp];
+    const long long w = (long long)blockIdx.x * FK_STREAM_WARPS + warp, W = (long long)gridDim.x * FK_STREAM_WARPS;
+    const float *k = a.rc.fkc_f;
+    const float TWO_PI = 6.283185307179586f;
+    const char *ang = reinterpret_cast<const char *>(a.angles);
+    const char *tgt = reinterpret_cast<const char *>(a.targets);
+    float2 *out = reinterpret_cast<float2 *>(a.err_out);
+    double err_sum = 0.0;
+    unsigned err_cnt = 0;
+    auto issue = [&](long long trip, int stage) {
+        if (trip < n_trips) {
+            const char *ga = ang + trip * 1024, *gt = tgt + trip * 768;
+            char *sa = reinterpret_cast<char *>(ring[stage].ang), *st = reinterpret_cast<char *>(ring[stage].tgt);
+            cp_async16(sa + lane * 16, ga + lane * 16);
+            cp_async16(sa + 512 + lane * 16, ga + 512 + lane * 16);
+            cp_async16(st + lane * 16, gt + lane * 16);
+            if (lane < 16)
+                cp_async16(st + 512 + lane * 16, gt + 512 + lane * 16);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");  // one group per trip, possibly empty: the wait below counts groups
+    };
+    auto row_error = [&](const float (&s)[4], const float (&c)[4], const float4 &th, float tx, float ty, float tz) {
+        float px, py, pz;
+        fk_planar_tail_position<float>(s, c, k[0], k[1], k[2], k[3], k[4], k[5], k[6], k[7], px, py, pz);
+        const float dx = px - tx, dy = py - ty, dz = pz - tz;
+        float err;
+        asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(err) : "f"(dx * dx + dy * dy + dz * dz));
+        const bool ok = !(fabsf(th.x) > TWO_PI) & !(fabsf(th.y) > TWO_PI) & !(fabsf(th.z) > TWO_PI) & !(fabsf(th.w) > TWO_PI);
+        return ok ? err : __int_as_float(0x7fc00000);
+    };
+#pragma unroll
+    for (int sidx = 0; sidx < FK_STREAM_STAGES - 1; ++sidx)
+        issue(w + sidx * W, sidx);
+    int stage = 0;
+    for (long long trip = w; trip < n_trips; trip += W) {
+        int ahead = stage + FK_STREAM_STAGES - 1;
+        ahead -= ahead >= FK_STREAM_STAGES ? FK_STREAM_STAGES : 0;
+        issue(trip + (FK_STREAM_STAGES - 1) * W, ahead);
+        asm volatile("cp.async.wait_group %0;" ::"n"(FK_STREAM_STAGES - 1) : "memory");
+        __syncwarp();
+        const float4 th0 = ring[stage].ang[2 * lane], th1 = ring[stage].ang[2 * lane + 1];
+        const float2 t0 = ring[stage].tgt[3 * lane], t1 = ring[stage].tgt[3 * lane + 1], t2 = ring[stage].tgt[3 * lane + 2];
+        __syncwarp();  // every lane has read its rows: the stage may be refilled by the next issue()
+        float s0[4], c0[4], s1[4], c1[4];
+        ikb_sincos2(th0.x, th1.x, s0[0], c0[0], s1[0], c1[0]);
+        ikb_sincos2(th0.y, th1.y, s0[1], c0[1], s1[1], c1[1]);
+        ikb_sincos2(th0.z, th1.z, s0[2], c0[2], s1[2], c1[2]);
+        ikb_sincos2(th0.w, th1.w, s0[3], c0[3], s1[3], c1[3]);
+        const float e0 = row_error(s0, c0, th0, t0.x, t0.y, t1.x);
+        const float e1 = row_error(s1, c1, th1, t1.y, t2.x, t2.y);
+        const long long p = trip * 32 + lane;
+        if (e0 != e0)
+            if (fabsf(th0.x) > TWO_PI || fabsf(th0.y) > TWO_PI || fabsf(th0.z) > TWO_PI || fabsf(th0.w) > TWO_PI)
+                atomicMin(&a.stats->first_fk_angle_range, a.index_base + 2 * p);
+        if (e1 != e1)
+            if (fabsf(th1.x) > TWO_PI || fabsf(th1.y) > TWO_PI || fabsf(th1.z) > TWO_PI || fabsf(th1.w) > TWO_PI)
+                atomicMin(&a.stats->first_fk_angle_range, a.index_base + 2 * p + 1);
+        if (out)
+            out[p] = make_float2(e0, e1);
+        float part = 0.f;
+        if (isfinite(e0)) { part += e0; ++err_cnt; }
+        if (isfinite(e1)) { part += e1; ++err_cnt; }
+        err_sum += (double)part;
+        stage = stage + 1 == FK_STREAM_STAGES ? 0 : stage + 1;
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    err_sum = ikb_warp_sum(err_sum);
+    err_cnt = ikb_warp_sum(err_cnt);
+    if (lane == 0 && err_cnt) {
         atomicAdd(&a.stats->sum_fk_error, err_sum);
         atomicAdd(&a.stats->n_fk_error, (unsigned long long)err_cnt);
     }
@@ -309,6 +435,35 @@ cudaError_t ikb_launch_fk(const void *angles, int angles_f64, long long n, long 
         alpha_ok = alpha_ok && !(rc.alpha[j] < -6.283185307179586) && !(rc.alpha[j] > 6.283185307179586);
     if (!angles_f64 && !xyz_f64 && targets && !pos_out && alpha_ok && ((uintptr_t)targets & 7) == 0 &&
         ((uintptr_t)err_out & 7) == 0 && n >= 2) {
+        static const bool use_stream = [] { const char *v = std::getenv("IKB_FK_STREAM"); return !v || v[0] != '0'; }();
+        const long long n_trips = n / 64;  // full trips of 32 pairs for the asynchronous-copy kernel
+        if (use_stream && n_trips >= 4LL * num_sms * FK_STREAM_WARPS && ((uintptr_t)targets & 15) == 0 &&
+            ((uintptr_t)angles & 15) == 0) {
+            const long long want = (n_trips + FK_STREAM_WARPS - 1) / FK_STREAM_WARPS, cap = (long long)num_sms * 4;
+            static const cudaError_t carve = cudaFuncSetAttribute(fk_error_stream_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                                                  (int)cudaSharedmemCarveoutMaxShared);
+            if (carve != cudaSuccess)
+                return carve;
+            fk_error_stream_kernel<<<(unsigned)(want < cap ? want : cap), FK_STREAM_WARPS * 32, 0, stream>>>(a, n_trips);
+            cudaError_t err = cudaGetLastError();
+            const long long done = n_trips * 64;
+            if (err != cudaSuccess || done == n)
+                return err;
+            // the last partial trip (< 64 rows): the pair kernel on the tail, same arithmetic
+            FkArgs t = a;
+            t.n = n - done;
+            t.index_base = index_base + done;
+            t.angles = reinterpret_cast<const float *>(angles) + 4 * done;
+            t.targets = reinterpret_cast<const float *>(targets) + 3 * done;
+            t.err_out = err_out ? reinterpret_cast<float *>(err_out) + done : nullptr;
+            if (t.n >= 2) {
+                fk_error_pairs_kernel<<<1, 256, 0, stream>>>(t);
+                return cudaGetLastError();
+            }
+            a = t;  // a single odd row: the generic kernel below
+            fk_kernel<float, false><<<1, 256, 0, stream>>>(a);
+            return cudaGetLastError();
+        }
         const unsigned pgrid = ikb_stream_grid(n / 2, num_sms, 256, FK_PAIR_MINB);
         fk_error_pairs_kernel<<<pgrid, 256, 0, stream>>>(a);
         return cudaGetLastError();

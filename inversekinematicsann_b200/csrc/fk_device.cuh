@@ -85,12 +85,14 @@ __device__ __forceinline__ void ikb_sincos2(float x0, float x1, float &s0, float
     float sp0, sp1, cp0, cp1;
     ikb_unpack2(SP, sp0, sp1);
     ikb_unpack2(CP, cp0, cp1);
+    // quadrant: odd k swaps sine and cosine, bit 1 of k (k + 1 for the cosine) flips the sign -- the flip as an XOR of
+    // the sign bit (bit 1 shifted to bit 31), which is what `(q & 2) ? -v : v` means for every v including 0 and NaN
     const float ss0 = (q0 & 1) ? cp0 : sp0, cc0 = (q0 & 1) ? sp0 : cp0;
     const float ss1 = (q1 & 1) ? cp1 : sp1, cc1 = (q1 & 1) ? sp1 : cp1;
-    s0 = (q0 & 2) ? -ss0 : ss0;
-    c0 = ((q0 + 1) & 2) ? -cc0 : cc0;
-    s1 = (q1 & 2) ? -ss1 : ss1;
-    c1 = ((q1 + 1) & 2) ? -cc1 : cc1;
+    s0 = __int_as_float(__float_as_int(ss0) ^ ((q0 << 30) & 0x80000000));
+    c0 = __int_as_float(__float_as_int(cc0) ^ (((q0 + 1) << 30) & 0x80000000));
+    s1 = __int_as_float(__float_as_int(ss1) ^ ((q1 << 30) & 0x80000000));
+    c1 = __int_as_float(__float_as_int(cc1) ^ (((q1 + 1) << 30) & 0x80000000));
 }
 
 // Closed form for arms whose joints 2..4 have alpha == 0 (see fk_position): the constants are passed as scalars so

@@ -159,3 +159,41 @@ def test_device_entry_points_fk_stats_only():
     eng.stats_reset_torch()
     eng.fabrik_solve_device(xyz, ang)
     assert eng.stats_fetch_torch().n_fk_error == 0
+
+
+def test_three_fk_error_kernels_agree_and_match_the_oracle():
+    """K3 has three code paths for ||FK(angles) - target||: the asynchronous-copy ring (large fp32 batches), the pair
+    kernel (its tail, small batches, unaligned buffers) and the generic kernel (positions wanted).  One batch large
+    enough for the ring plus a ragged tail: all three against each other and against the fp64 oracle, and the guard of
+    forward.py:23-25 reports the same first offending row on every path."""
+    import torch
+    from inversekinematicsann_b200.kinematics._shared import get_engine
+    from oracle import c_oracle
+    eng = get_engine()
+    n = 1_000_037                                   # 15 625 full trips of 64 rows + 37 rows for the pair kernel
+    g = torch.Generator(device="cuda").manual_seed(3)
+    ang = (torch.rand(n, 4, device="cuda", generator=g) * 2 - 1) * 3.0
+    tgt = torch.rand(n, 3, device="cuda", generator=g) * 6 - 3
+    err_ring = torch.empty(n, device="cuda")
+    eng.stats_reset_torch()
+    eng.fk_device(ang, targets=tgt, err=err_ring)                      # ring + pair tail
+    st_ring = eng.stats_fetch_torch()
+    err_pair = torch.empty(n - 1, device="cuda")
+    eng.fk_device(ang[1:], targets=tgt[1:], err=err_pair)              # 4-byte offset: unaligned -> generic / pair path
+    pos = torch.empty(n, 3, device="cuda")
+    err_gen = torch.empty(n, device="cuda")
+    eng.fk_device(ang, targets=tgt, pos=pos, err=err_gen)              # positions wanted -> generic kernel
+    torch.cuda.synchronize()
+    assert (err_ring[1:] - err_pair).abs().max().item() <= 2e-6
+    assert (err_ring - err_gen).abs().max().item() <= 2e-6
+    pick = torch.arange(0, n, 97, device="cuda")
+    _, _, want = c_oracle.fk_positions(ang[pick].double().cpu().numpy(), targets=tgt[pick].double().cpu().numpy())
+    assert np.abs(err_ring[pick].cpu().numpy() - want).max() <= 1e-5
+    assert st_ring.n_fk_error == n and abs(st_ring.mean_fk_error - err_ring.double().mean().item()) <= 1e-6
+    bad = ang.clone()
+    bad[777_777, 2] = 6.5                            # outside [-2 pi, 2 pi]
+    bad[900_001, 0] = -7.0
+    eng.stats_reset_torch()
+    eng.fk_device(bad, targets=tgt, err=err_ring)
+    st = eng.stats_fetch_torch()
+    assert st.first_fk_angle_range == 777_777 and torch.isnan(err_ring[777_777]).item()
