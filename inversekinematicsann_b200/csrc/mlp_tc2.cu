@@ -19,6 +19,7 @@
 #include <cuda_fp16.h>
 
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -38,8 +39,22 @@ namespace {
 
 constexpr int ROWS = 128;             // targets per CTA tile = UMMA M
 constexpr int GRAN_BYTES = 16384;     // x_lo granule: 128 rows x 64 k x fp16
-constexpr int WTILE_BYTES = 32768;    // weight tile: up to 256 features x 64 k x fp16
-constexpr int W_STAGES = 3;
+// k extent of one weight tile (compile-time): 64 (default: rows of 128 B, 128-byte swizzle, three 32 KB ring stages) or 32
+// (rows of 64 B, 64-byte swizzle, six 16 KB stages: the same 96 KB with more of the ring in flight at any time).
+// Measured on B200, 1 M rows: 14.24 ms (64) against 14.45 ms (32), identical results -- the issuer's waits for weights
+// drop by a fifth with the finer stages, but twice as many commits / waits on the single issuing thread cost as much,
+// and the kernel runs at the power-capped clock (1.58 GHz, 88 % of what a cuBLAS bf16 GEMM sustains under the same cap)
+// either way.
+#ifndef IKB_TS_WK
+#define IKB_TS_WK 64
+#endif
+constexpr int WK = IKB_TS_WK;                   // 64: rows of 128 B, 128-byte swizzle; 32: rows of 64 B, 64-byte swizzle
+static_assert(WK == 64 || WK == 32, "weight tiles are 64 or 32 k wide");
+constexpr int WROW_BYTES = WK * 2;
+constexpr int WKSTEPS = WK / 16;                // UMMA K steps per weight tile
+constexpr int WSUB = 64 / WK;                   // weight tiles per x_lo granule (64 k)
+constexpr int WTILE_BYTES = 256 * WROW_BYTES;   // weight tile: up to 256 features x WK k x fp16
+constexpr int W_RING_BYTES = 98304;             // weight ring: 96 KB = 3 / 6 stages of a whole tile (half tiles for CTA pairs: twice as many)
 #ifndef IKB_TS_EPI_WARPS
 #define IKB_TS_EPI_WARPS 16
 #endif
@@ -116,6 +131,46 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
         "}\n" ::"r"(smem_u32(bar)), "r"(parity)
         : "memory");
 }
+// ---- CTA pairs (cta_group::2; opt-in with IKB_TS_CLUSTER=2): two CTAs on the SMs of one TPC run ONE M = 256 MMA: each
+// holds 128 batch rows (its own x_hi in TMEM, x_lo in shared memory, accumulator in TMEM) and HALF of every weight tile
+// (128 of the 256 features), which the tensor cores of both SMs read.  Per SM that halves the weight bytes TMA writes
+// into shared memory and the L2 -> SM traffic.  Bit-identical results -- and SLOWER on B200: 17.4 ms against 13.9 ms per
+// 1 M rows.  The issuer's time per layer grows from 37 k to 55 k cycles and stays there with a third or two thirds of
+// the MMAs removed (timing experiments with -DIKB_DBG_SKIP_SS / _TS), i.e. it is not tensor throughput but the longer
+// hand-off chain of every ring stage (multicast commit -> both producers -> TMA -> the peer's "landed" forwarded by a
+// remote mbarrier arrive -> issuer) and of every accumulator / activation barrier, which now waits for two epilogues.
+// Kept as a tested switch, not the default.
+__device__ __forceinline__ uint32_t cluster_ctarank()
+{
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all()
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the mbarrier at the same shared-memory offset in CTA `rank` of the cluster
+__device__ __forceinline__ void mbar_arrive_cluster(uint64_t *bar, uint32_t rank)
+{
+    uint32_t remote;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(bar)), "r"(rank));
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+}
+// wait that also acquires at cluster scope (the arrivals come from the peer CTA)
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t *bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "TSC_WAIT:\n"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra TSC_DONE;\n"
+        "bra TSC_WAIT;\n"
+        "TSC_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+}
 __device__ __forceinline__ void tma_load_1d(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
 {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
@@ -129,6 +184,12 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr)  // K-major, 128B swizzle, 8-row groups 1024 B apart
 {
     return (uint64_t)((smem_addr >> 4) & 0x3FFF) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+// weight tiles: K-major rows of WROW_BYTES, 8-row groups 8 * WROW_BYTES apart, layout type 2 (128B swizzle) / 4 (64B)
+__device__ __forceinline__ uint64_t make_desc_w(uint32_t smem_addr)
+{
+    return (uint64_t)((smem_addr >> 4) & 0x3FFF) | (1ull << 16) | ((uint64_t)(8 * WROW_BYTES >> 4) << 32) | (1ull << 46) |
+           ((WK == 64 ? 2ull : 4ull) << 61);
 }
 // D[tmem] (+)= A[smem] * B[smem]
 __device__ __forceinline__ void umma_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc)
@@ -151,6 +212,48 @@ __device__ __forceinline__ void umma_commit(uint64_t *bar)
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                  : "memory");
 }
+// the same three for a CTA pair: issued by the leader CTA only, M = 256 over both CTAs; the commit arrives on the barrier
+// at this shared-memory offset in BOTH CTAs
+__device__ __forceinline__ void umma2_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc)
+{
+    asm volatile(
+        "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n}\n" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc)
+        : "memory");
+}
+__device__ __forceinline__ void umma2_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t acc)
+{
+    asm volatile(
+        "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n}\n" ::"r"(d_tmem),
+        "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(acc)
+        : "memory");
+}
+__device__ __forceinline__ void umma2_commit(uint64_t *bar)
+{
+    asm volatile(
+        "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+        "h"((unsigned short)3)
+        : "memory");
+}
+template <int NCTA>
+__device__ __forceinline__ void mma_ss(uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc)
+{
+#ifndef IKB_DBG_SKIP_SS  // timing experiments only: results are wrong without this product
+    if (NCTA == 2) umma2_ss(d, a, b, idesc, acc); else umma_ss(d, a, b, idesc, acc);
+#endif
+}
+template <int NCTA>
+__device__ __forceinline__ void mma_ts(uint32_t d, uint32_t a, uint64_t b, uint32_t idesc, uint32_t acc)
+{
+#ifndef IKB_DBG_SKIP_TS
+    if (NCTA == 2) umma2_ts(d, a, b, idesc, acc); else umma_ts(d, a, b, idesc, acc);
+#endif
+}
+template <int NCTA>
+__device__ __forceinline__ void mma_commit(uint64_t *bar)
+{
+    if (NCTA == 2) umma2_commit(bar); else umma_commit(bar);
+}
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32])
 {
     asm volatile(
@@ -168,6 +271,14 @@ __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.
 __device__ __host__ __forceinline__ int swz_off(int row, int k)  // [rows x 64] fp16 K-major tile, 128B swizzle
 {
     return row * 128 + ((((k >> 3) ^ (row & 7)) & 7) << 4) + ((k & 7) << 1);
+}
+// byte offset of element (row, k) in a weight tile [rows x WK] fp16, K-major: 128-byte swizzle for 128-byte rows (16-byte
+// chunk index ^= row & 7), 64-byte swizzle for 64-byte rows (chunk index ^= (row >> 1) & 3: address bits [4,6) ^= [7,9))
+__device__ __host__ __forceinline__ int wswz_off(int row, int k)
+{
+    if (WK == 64)
+        return swz_off(row, k);
+    return row * 64 + ((((k >> 3) ^ (row >> 1)) & 3) << 4) + ((k & 7) << 1);
 }
 
 // tanh with the accumulator scale folded into the exponent and X_SCALE folded into the result:
@@ -232,8 +343,19 @@ struct EpiCtx {
     uint64_t *a_free, *act_ready;
     uint32_t tmem_base, lane_base;
     int row, lane, HP;
+    int pair_peer;         // this CTA is rank 1 of a CTA pair: epilogue -> MMA barriers live in rank 0
     float in0, in1, in2;   // scaled inputs of this thread's row (first layer)
 };
+
+// epilogue -> MMA issuer ("these activations are stored" / "the accumulator is drained"): the issuer lives in the
+// leader CTA of a pair, so the peer's epilogue warps arrive there
+__device__ __forceinline__ void epi_arrive(const EpiCtx &cx, uint64_t *bar)
+{
+    if (cx.pair_peer)
+        mbar_arrive_cluster(bar, 0);
+    else
+        mbar_arrive(bar);
+}
 
 // Layer 1 (3 -> HP) for one thread: `ncols` features starting at f0, a rolled loop over chunks of 8 features
 // stored at once (nothing reads the activation buffers while a tile's first layer runs), or fed to the output sums
@@ -282,7 +404,7 @@ __device__ __forceinline__ void first_layer_half(const EpiCtx &cx, int f0, int n
     tc_fence_before();
     __syncwarp();
     if (cx.lane == 0)
-        mbar_arrive(&cx.act_ready[ready_idx]);
+        epi_arrive(cx, &cx.act_ready[ready_idx]);
 }
 
 // One N half of one hidden layer for one thread.  The thread owns QMAX groups of 32 accumulator columns; group q
@@ -355,7 +477,7 @@ __device__ __forceinline__ void finish_half(const EpiCtx &cx, uint32_t (&d)[QMAX
         tc_fence_before();
         __syncwarp();
         if (cx.lane == 0)
-            mbar_arrive(&cx.act_ready[ready_base + q]);
+            epi_arrive(cx, &cx.act_ready[ready_base + q]);
     };
     if (last_hidden) {
 #pragma unroll
@@ -391,62 +513,83 @@ __device__ __forceinline__ void finish_half(const EpiCtx &cx, uint32_t (&d)[QMAX
     }
 }
 
+// NCTA = 1: one CTA per SM on its own.  NCTA = 2: CTA pairs (clusters of two), see the cluster helpers above; rank 0
+// is the leader (it issues every MMA), each CTA of a pair works on its own tile of 128 rows.
+template <int NCTA>
 __global__ void __launch_bounds__(THREADS, 1) mlp_tc2_kernel(const Tc2Args a)
 {
+    constexpr int STAGE_BYTES = WTILE_BYTES / NCTA;        // a CTA of a pair holds half of every weight tile
+    constexpr int W_STAGES = W_RING_BYTES / STAGE_BYTES;   // 3 whole tiles or 6 half tiles
     extern __shared__ __align__(1024) unsigned char smem[];
     const Tc2Net &net = a.net;
     const int HP = net.hp, KG = HP >> 6, NHALF = (HP + 255) >> 8, NM = net.n_mma_layers;
+    const int KT = HP / WK;                                        // weight k tiles per layer
     unsigned char *xlo = smem;                                     // KG granules of x_lo
-    unsigned char *wring = smem + (size_t)KG * GRAN_BYTES;          // W_STAGES weight tiles
-    float *s_io = reinterpret_cast<float *>(wring + (size_t)W_STAGES * WTILE_BYTES);  // [128][4] inputs / output partials
+    unsigned char *wring = smem + (size_t)KG * GRAN_BYTES;          // W_STAGES weight (half) tiles
+    float *s_io = reinterpret_cast<float *>(wring + (size_t)W_RING_BYTES);  // [128][4] inputs / output partials
     uint64_t *bars = reinterpret_cast<uint64_t *>(s_io + ROWS * 4);
-    uint64_t *w_full = bars, *w_empty = bars + W_STAGES;
-    uint64_t *d_full = w_empty + W_STAGES, *d_empty = d_full + 1;   // the single accumulator: MMA <-> epilogue
+    static_assert(W_STAGES <= 12, "barrier block holds 12 stages");
+    uint64_t *w_full = bars, *w_empty = bars + 12, *w_peer = bars + 24;  // w_peer (leader): the peer's half of a stage has landed
+    uint64_t *d_full = bars + 36, *d_empty = d_full + 1;            // the single accumulator: MMA <-> epilogue
     uint64_t *act_ready = d_empty + 1;                              // [4] epilogue -> MMA: 128 features (2 k chunks) of the next input stored
     uint64_t *a_free = act_ready + 4;                               // MMA -> epilogue: this layer's input is dead
     uint32_t *s_tmem = reinterpret_cast<uint32_t *>(a_free + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = NCTA == 2 ? cluster_ctarank() : 0u;       // 0 = leader of the pair
     if (threadIdx.x == 0) {
         for (int i = 0; i < W_STAGES; ++i) {
             mbar_init(&w_full[i], 1);
             mbar_init(&w_empty[i], 1);
+            mbar_init(&w_peer[i], 1);
         }
         mbar_init(d_full, 1);
-        mbar_init(d_empty, N_EPI_WARPS);
+        mbar_init(d_empty, N_EPI_WARPS * NCTA);      // a pair: the epilogue warps of both CTAs arrive in the leader
         for (int i = 0; i < 4; ++i)
-            mbar_init(&act_ready[i], N_EPI_WARPS);
+            mbar_init(&act_ready[i], N_EPI_WARPS * NCTA);
         mbar_init(a_free, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "r"(512));
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+        if (NCTA == 2) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "r"(512));
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "r"(512));
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+        }
     }
     tc_fence_before();
     __syncthreads();
+    if (NCTA == 2)
+        cluster_sync_all();   // both CTAs' barriers are initialised before anybody arrives on a remote one
     tc_fence_after();
     const uint32_t tmem_base = *s_tmem;
     const long long n_tiles = (a.n + ROWS - 1) / ROWS;
+    // both CTAs of a pair run the same number of trips (the MMAs span both); a tile index past the end is an empty tile
+    const long long n_groups = (n_tiles + NCTA - 1) / NCTA, group0 = blockIdx.x / NCTA, group_stride = gridDim.x / NCTA;
 
     if (warp == 0) {
         // ===== TMA producer: the weight tiles of every (layer, N half) in the order the issuer consumes them =====
         // arena layout: [layer][N half][k chunk][hi | lo] tiles of WTILE_BYTES.
-        // interleaved order: kc0 hi, kc0 lo, kc1 hi, ...; corrections first: (kc hi, kc lo) for all kc, then kc hi again
+        // interleaved order: kc0 hi, kc0 lo, kc1 hi, ...; corrections first: (kc hi, kc lo) for all kc, then kc hi again.
+        // A CTA of a pair loads its half of the tile's features: rows [rank * nfeat / 2, ...) of the swizzled image, which
+        // is a valid image of its own (the swizzle pattern repeats every 8 rows).
         if (lane == 0) {
             int s = 0;
             uint32_t ph = 1;
             const unsigned char *base = reinterpret_cast<const unsigned char *>(net.w_tiles);
-            for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            for (long long g = group0; g < n_groups; g += group_stride) {
                 for (int mh = 0; mh < NM * NHALF; ++mh) {
-                    const unsigned char *half_base = base + (size_t)mh * KG * 2 * WTILE_BYTES;
-                    const uint32_t bytes = (uint32_t)min(256, HP - 256 * (mh % NHALF)) * 128u;
-                    for (int t = 0; t < KG * TILES_PER_KC; ++t) {
-                        // t < 2 KG: tile t of the half as stored; after that the hi tile of k chunk t - 2 KG
-                        const int src_tile = t < 2 * KG ? t : 2 * (t - 2 * KG);
+                    const unsigned char *half_base = base + (size_t)mh * KT * 2 * WTILE_BYTES;
+                    const uint32_t bytes = (uint32_t)min(256, HP - 256 * (mh % NHALF)) * (uint32_t)WROW_BYTES / NCTA;
+                    for (int t = 0; t < KT * TILES_PER_KC; ++t) {
+                        // t < 2 KT: tile t of the half as stored; after that the hi tile of k tile t - 2 KT
+                        const int src_tile = t < 2 * KT ? t : 2 * (t - 2 * KT);
                         mbar_wait(&w_empty[s], ph);
                         mbar_expect_tx(&w_full[s], bytes);
-                        tma_load_1d(wring + (size_t)s * WTILE_BYTES, half_base + (size_t)src_tile * WTILE_BYTES, bytes, &w_full[s]);
+                        tma_load_1d(wring + (size_t)s * STAGE_BYTES, half_base + (size_t)src_tile * WTILE_BYTES + rank * bytes,
+                                    bytes, &w_full[s]);
                         if (++s == W_STAGES) {
                             s = 0;
                             ph ^= 1;
@@ -455,80 +598,100 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_tc2_kernel(const Tc2Args a)
                 }
             }
         }
-    } else if (warp == 1) {
-        // ===== MMA issuer =====
+    } else if (warp == 1 && rank != 0) {
+        // ===== peer CTA of a pair: tell the leader's issuer when this CTA's half of a weight stage has landed =====
         if (lane == 0) {
-            const uint64_t b_desc_base = make_desc(smem_u32(wring));
+            int s = 0;
+            uint32_t ph = 0;
+            for (long long g = group0; g < n_groups; g += group_stride)
+                for (int t = 0; t < NM * NHALF * KT * TILES_PER_KC; ++t) {
+                    mbar_wait(&w_full[s], ph);
+                    mbar_arrive_cluster(&w_peer[s], 0);
+                    if (++s == W_STAGES) { s = 0; ph ^= 1; }
+                }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer (the leader CTA of a pair issues for both) =====
+        if (lane == 0) {
+            const uint64_t b_desc_base = make_desc_w(smem_u32(wring));
             const uint64_t xlo_desc_base = make_desc(smem_u32(xlo));
-            constexpr uint32_t GRAN_DESC = GRAN_BYTES >> 4, WTILE_DESC = WTILE_BYTES >> 4;
+            constexpr uint32_t GRAN_DESC = GRAN_BYTES >> 4, WTILE_DESC = STAGE_BYTES >> 4;
             const uint32_t d_tmem = tmem_base + TMEM_D_COL, a_tmem = tmem_base + TMEM_A_COL;
             int s = 0;
             uint32_t ph = 0, use = 0, duse = 0;  // use: MMA layers issued so far, duse: accumulator uses so far
+            auto wait_stage = [&]() {            // this stage's weights are in shared memory (of both CTAs of a pair)
+                DBG_T0();
+                mbar_wait(&w_full[s], ph);
+                if (NCTA == 2)
+                    mbar_wait_cluster(&w_peer[s], ph);
+                DBG_ADD(1);
+                tc_fence_after();
+            };
+            auto next_stage = [&]() {
+                mma_commit<NCTA>(&w_empty[s]);
+                if (++s == W_STAGES) { s = 0; ph ^= 1; }
+            };
 #ifdef IKB_TC_DEBUG
             const long long _tstart = clock64();
 #endif
-            for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            for (long long g = group0; g < n_groups; g += group_stride) {
                 for (int m = 0; m < NM; ++m, ++use) {
                     for (int nh = 0; nh < NHALF; ++nh, ++duse) {
                         const uint32_t nfeat = (uint32_t)min(256, HP - 256 * nh);
-                        // D fp32, A/B fp16, K-major, N = features of this half, M = 128
-                        const uint32_t idesc = (1u << 4) | ((nfeat >> 3) << 17) | ((128u >> 4) << 24);
-                        { DBG_T0(); mbar_wait(d_empty, (duse & 1) ^ 1); DBG_ADD(3); }  // the epilogue has drained the accumulator
+                        // D fp32, A/B fp16, K-major, N = features of this half, M = 128 rows per CTA
+                        const uint32_t idesc = (1u << 4) | ((nfeat >> 3) << 17) | (((128u * NCTA) >> 4) << 24);
+                        // the epilogue (of both CTAs) has drained the accumulator
+                        { DBG_T0(); if (NCTA == 2) mbar_wait_cluster(d_empty, (duse & 1) ^ 1); else mbar_wait(d_empty, (duse & 1) ^ 1); DBG_ADD(3); }
                         tc_fence_after();
-                        for (int kc = 0; kc < KG; ++kc) {
-                            if (nh == 0 && (kc & 1) == 0) {  // features 64 kc .. 64 kc + 127 of this layer's input are stored
-                                { DBG_T0(); mbar_wait(&act_ready[kc >> 1], use & 1); DBG_ADD(2); }
+                        for (int kt = 0; kt < KT; ++kt) {
+                            const int k0 = kt * WK;
+                            if (nh == 0 && (k0 & 127) == 0) {  // features k0 .. k0 + 127 of this layer's input are stored
+                                { DBG_T0(); if (NCTA == 2) mbar_wait_cluster(&act_ready[k0 >> 7], use & 1); else mbar_wait(&act_ready[k0 >> 7], use & 1); DBG_ADD(2); }
                                 tc_fence_after();
                             }
-                            const uint32_t a_cols = a_tmem + kc * 32;  // 64 k = 32 columns of packed fp16 pairs
-                            const uint64_t xlo_desc = xlo_desc_base + (uint64_t)(kc * GRAN_DESC);
+                            const uint32_t a_cols = a_tmem + (k0 >> 1);  // two k per 32-bit column
+                            const uint64_t xlo_desc = xlo_desc_base + (uint64_t)((kt / WSUB) * GRAN_DESC + (kt % WSUB) * (WK >> 3));
                             // w_hi tile
-                            { DBG_T0(); mbar_wait(&w_full[s], ph); DBG_ADD(1); }
-                            tc_fence_after();
+                            wait_stage();
                             uint64_t b_desc = b_desc_base + (uint64_t)(s * WTILE_DESC);
 #if IKB_TS_CORR_FIRST
                             // corrections first: x_lo (smem) w_hi opens the accumulator, x_hi w_hi waits for the second pass
 #pragma unroll
-                            for (int ks = 0; ks < 4; ++ks)
-                                umma_ss(d_tmem, xlo_desc + 2 * ks, b_desc + 2 * ks, idesc, (kc | ks) != 0);
+                            for (int ks = 0; ks < WKSTEPS; ++ks)
+                                mma_ss<NCTA>(d_tmem, xlo_desc + 2 * ks, b_desc + 2 * ks, idesc, (kt | ks) != 0);
 #else
                             // x_hi (TMEM) and x_lo (smem) both multiply it
 #pragma unroll
-                            for (int ks = 0; ks < 4; ++ks)
-                                umma_ts(d_tmem, a_cols + ks * 8, b_desc + 2 * ks, idesc, (kc | ks) != 0);
+                            for (int ks = 0; ks < WKSTEPS; ++ks)
+                                mma_ts<NCTA>(d_tmem, a_cols + ks * 8, b_desc + 2 * ks, idesc, (kt | ks) != 0);
 #pragma unroll
-                            for (int ks = 0; ks < 4; ++ks)
-                                umma_ss(d_tmem, xlo_desc + 2 * ks, b_desc + 2 * ks, idesc, 1);
+                            for (int ks = 0; ks < WKSTEPS; ++ks)
+                                mma_ss<NCTA>(d_tmem, xlo_desc + 2 * ks, b_desc + 2 * ks, idesc, 1);
 #endif
-                            umma_commit(&w_empty[s]);
-                            if (++s == W_STAGES) { s = 0; ph ^= 1; }
+                            next_stage();
                             // w_lo tile: only x_hi multiplies it (x_lo w_lo is below fp32 resolution)
-                            { DBG_T0(); mbar_wait(&w_full[s], ph); DBG_ADD(1); }
-                            tc_fence_after();
+                            wait_stage();
                             b_desc = b_desc_base + (uint64_t)(s * WTILE_DESC);
 #pragma unroll
-                            for (int ks = 0; ks < 4; ++ks)
-                                umma_ts(d_tmem, a_cols + ks * 8, b_desc + 2 * ks, idesc, 1);
-                            umma_commit(&w_empty[s]);
-                            if (++s == W_STAGES) { s = 0; ph ^= 1; }
+                            for (int ks = 0; ks < WKSTEPS; ++ks)
+                                mma_ts<NCTA>(d_tmem, a_cols + ks * 8, b_desc + 2 * ks, idesc, 1);
+                            next_stage();
                         }
 #if IKB_TS_CORR_FIRST
                         // main product last: its 32 steps are the only ones that truncate at the sum's full size
-                        for (int kc = 0; kc < KG; ++kc) {
-                            const uint32_t a_cols = a_tmem + kc * 32;
-                            { DBG_T0(); mbar_wait(&w_full[s], ph); DBG_ADD(1); }
-                            tc_fence_after();
+                        for (int kt = 0; kt < KT; ++kt) {
+                            const uint32_t a_cols = a_tmem + ((kt * WK) >> 1);
+                            wait_stage();
                             const uint64_t b_desc = b_desc_base + (uint64_t)(s * WTILE_DESC);
 #pragma unroll
-                            for (int ks = 0; ks < 4; ++ks)
-                                umma_ts(d_tmem, a_cols + ks * 8, b_desc + 2 * ks, idesc, 1);
-                            umma_commit(&w_empty[s]);
-                            if (++s == W_STAGES) { s = 0; ph ^= 1; }
+                            for (int ks = 0; ks < WKSTEPS; ++ks)
+                                mma_ts<NCTA>(d_tmem, a_cols + ks * 8, b_desc + 2 * ks, idesc, 1);
+                            next_stage();
                         }
 #endif
-                        umma_commit(d_full);
+                        mma_commit<NCTA>(d_full);
                     }
-                    umma_commit(a_free);  // every read of this layer's x_hi / x_lo has completed
+                    mma_commit<NCTA>(a_free);  // every read of this layer's x_hi / x_lo has completed
                 }
             }
 #ifdef IKB_TC_DEBUG
@@ -544,8 +707,8 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_tc2_kernel(const Tc2Args a)
         const int et = ew * 32 + lane;
         const uint32_t lane_base = (uint32_t)(sub * 32) << 16;
         uint32_t use = 0, duse = 0;
-        for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-            const long long row0 = tile * ROWS;
+        for (long long g = group0; g < n_groups; g += group_stride) {
+            const long long row0 = (g * NCTA + rank) * ROWS;   // past the end for the odd CTA of the last pair: an empty tile
             // ---- inputs: x_scaler.transform in fp64 -> fp32 (ann.py:72), workspace limits (inverse.py:154) ----
             if (et < ROWS) {
                 const long long i = row0 + et;
@@ -568,6 +731,7 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_tc2_kernel(const Tc2Args a)
             EpiCtx cx;
             cx.net = &net; cx.xlo = xlo; cx.a_free = a_free; cx.act_ready = act_ready; cx.tmem_base = tmem_base;
             cx.lane_base = lane_base; cx.row = row; cx.lane = lane; cx.HP = HP; cx.in0 = in0; cx.in1 = in1; cx.in2 = in2;
+            cx.pair_peer = rank != 0;
             // ---- layer 1 (3 -> HP) on the CUDA cores ----
             for (int nh = 0; nh < NHALF; ++nh) {
                 const int ngroups = min(256, HP - 256 * nh) / (32 * CW);
@@ -595,7 +759,7 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_tc2_kernel(const Tc2Args a)
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0)
-                        mbar_arrive(d_empty);
+                        epi_arrive(cx, d_empty);
                     finish_half(cx, d, 256 * nh + 32 * ch, ngroups, m == NM - 1, nh + 1 < NHALF, use & 1, 2 * nh, oscale,
                                 bias, out_acc);
 #ifdef IKB_TC_DEBUG
@@ -640,13 +804,19 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_tc2_kernel(const Tc2Args a)
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 1)
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+    if (NCTA == 2)
+        cluster_sync_all();   // the peer may still read this CTA's shared memory / arrive on its barriers until here
+    if (warp == 1) {
+        if (NCTA == 2)
+            asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+        else
+            asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+    }
 }
 
 size_t tc2_smem_bytes(int hp)
 {
-    return (size_t)(hp / 64) * GRAN_BYTES + (size_t)W_STAGES * WTILE_BYTES + ROWS * 4 * sizeof(float) + 16 * 8 + 64;
+    return (size_t)(hp / 64) * GRAN_BYTES + (size_t)W_RING_BYTES + ROWS * 4 * sizeof(float) + 48 * 8 + 64;
 }
 
 }  // namespace
@@ -685,9 +855,9 @@ int ikb_mlp_tc2_pack(IkbMlpTc2 &t, int n_layers, const int *dims, const float *c
     for (int l = 1; l <= nh; ++l)
         hmax = dims[l] > hmax ? dims[l] : hmax;
     const int hp = ((hmax + 127) / 128) * 128;
-    const int KG = hp / 64, NHALF = (hp + 255) / 256, NM = nh - 1;
+    const int KT = hp / WK, NHALF = (hp + 255) / 256, NM = nh - 1;
     const size_t tile_halfs = WTILE_BYTES / sizeof(__half);
-    const size_t n_tiles = (size_t)NM * NHALF * KG * 2;
+    const size_t n_tiles = (size_t)NM * NHALF * KT * 2;
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) / 256 * 256; return o; };
     const size_t o_tiles = take((n_tiles ? n_tiles : 1) * WTILE_BYTES);
@@ -740,16 +910,16 @@ int ikb_mlp_tc2_pack(IkbMlpTc2 &t, int n_layers, const int *dims, const float *c
         const int acc_steps = (IKB_TS_CORR_FIRST ? 1 : 3) * ((fin + (bias_row >= 0 ? 1 : 0) + 15) / 16);
         oscale[m] = (float)(ikb_tc_truncation_compensation(acc_steps) / ((double)sw * X_SCALE));
         for (int nhalf = 0; nhalf < NHALF; ++nhalf)
-            for (int kc = 0; kc < KG; ++kc) {
-                __half *hi = tiles + (((size_t)(m * NHALF + nhalf) * KG + kc) * 2 + 0) * tile_halfs;
+            for (int kt = 0; kt < KT; ++kt) {
+                __half *hi = tiles + (((size_t)(m * NHALF + nhalf) * KT + kt) * 2 + 0) * tile_halfs;
                 __half *lo = hi + tile_halfs;
                 const int nfeat = std::min(256, hp - 256 * nhalf);
                 for (int r = 0; r < nfeat; ++r)
-                    for (int c = 0; c < 64; ++c) {
-                        const int f = nhalf * 256 + r, k = kc * 64 + c;
+                    for (int c = 0; c < WK; ++c) {
+                        const int f = nhalf * 256 + r, k = kt * WK + c;
                         const float w = weight_at(l, k, f) * sw;
                         const __half h = __float2half_rn(w);
-                        const int o = swz_off(r, c) / 2;
+                        const int o = wswz_off(r, c) / 2;
                         hi[o] = h;
                         lo[o] = __float2half_rn(w - __half2float(h));
                     }
@@ -784,7 +954,9 @@ int ikb_mlp_tc2_pack(IkbMlpTc2 &t, int n_layers, const int *dims, const float *c
         n.mean_x[j] = mean_x[j];
         n.scale_x[j] = scale_x[j];
     }
-    ce = cudaFuncSetAttribute(mlp_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc2_smem_bytes(hp));
+    ce = cudaFuncSetAttribute(mlp_tc2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc2_smem_bytes(hp));
+    if (ce == cudaSuccess)
+        ce = cudaFuncSetAttribute(mlp_tc2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc2_smem_bytes(hp));
     if (ce != cudaSuccess) {
         err = std::string("ikb_mlp_load (TS smem attribute): ") + cudaGetErrorString(ce);
         return IKB_ERR_CUDA;
@@ -806,9 +978,29 @@ int ikb_mlp_tc2_launch(const IkbMlpTc2 &t, const void *xyz, int xyz_f64, long lo
     a.fk_err = fk_err_out; a.fk_stats = fk_stats;
     a.stats = stats; a.rc = rc; a.net = t.net;
     const long long tiles = (n + ROWS - 1) / ROWS;
-    const unsigned grid = (unsigned)(tiles < num_sms ? tiles : num_sms);
-    mlp_tc2_kernel<<<grid, THREADS, tc2_smem_bytes(t.net.hp), stream>>>(a);
-    const cudaError_t ce = cudaGetLastError();
+    // CTA pairs (IKB_TS_CLUSTER=2; off by default: measured slower): clusters of two CTAs on the
+    // SMs of one TPC, an even grid
+    static const bool pairs = [] { const char *v = std::getenv("IKB_TS_CLUSTER"); return v && v[0] == '2'; }();
+    cudaError_t ce;
+    if (pairs && num_sms >= 2) {
+        const long long groups = (tiles + 1) / 2;
+        const unsigned grid = 2u * (unsigned)(groups < num_sms / 2 ? groups : num_sms / 2);
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(grid);
+        cfg.blockDim = dim3(THREADS);
+        cfg.dynamicSmemBytes = tc2_smem_bytes(t.net.hp);
+        cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        ce = cudaLaunchKernelEx(&cfg, mlp_tc2_kernel<2>, a);
+    } else {
+        const unsigned grid = (unsigned)(tiles < num_sms ? tiles : num_sms);
+        mlp_tc2_kernel<1><<<grid, THREADS, tc2_smem_bytes(t.net.hp), stream>>>(a);
+        ce = cudaGetLastError();
+    }
     if (ce != cudaSuccess) {
         err = std::string("mlp_tc2_kernel launch: ") + cudaGetErrorString(ce);
         return IKB_ERR_CUDA;

@@ -188,3 +188,25 @@ def test_accumulator_truncation_compensation_matters(monkeypatch):
     # (corrections-first accumulation leaves 32 full-size truncating steps per output instead of 96, so the bias to
     #  correct is a third of round 1's: measured 7.3e-7 without vs 2.3e-7 with the correction)
     assert e_off > 2 * e_on and e_off > 5e-7
+
+
+def test_cta_pair_mode_is_bit_identical(tmp_path):
+    """IKB_TS_CLUSTER=2 runs the default tensor-core mode on CTA pairs (tcgen05 cta_group::2, M = 256 over two SMs, each
+    CTA streaming half of every weight tile): the same MMAs in the same order per row, so the outputs must be the same
+    bits as the single-CTA kernel's, including a ragged last pair (an odd number of 128-row tiles)."""
+    import os
+    import subprocess
+    import sys
+    xyz = _points(128 * 301 + 77, seed=31).astype(np.float32)      # 302 tiles: the last pair has one real tile
+    single = _trained("fp16x3_ts").ikine(xyz, as_array=True)
+    np.save(tmp_path / "xyz.npy", xyz)
+    code = ("import sys, os, numpy as np; sys.path.insert(0, sys.argv[1]);"
+            "from inversekinematicsann_b200.kinematics.inverse import AnnInverseKinematics as A;"
+            "from inversekinematicsann_b200.robot.robot import SixDOFRobot as R;"
+            "ann = A(R.dh_matrix, R.links_lengths, R.effector_workspace_limits);"
+            "ann.load_model(os.path.join(sys.argv[1], 'models', 'roboarm_b200_r01.h5'));"
+            "np.save(sys.argv[3], ann.ikine(np.load(sys.argv[2]), as_array=True))")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    subprocess.run([sys.executable, "-c", code, root, str(tmp_path / "xyz.npy"), str(tmp_path / "pairs.npy")],
+                   env=dict(os.environ, IKB_TS_CLUSTER="2"), check=True, timeout=600)
+    assert np.array_equal(single, np.load(tmp_path / "pairs.npy"))
