@@ -95,9 +95,12 @@ WORKLOAD = ("BASELINE configs[2]: FABRIK on 100M cube_random targets per GPU, fu
 
 # ---- CPU arm (oracle port) -----------------------------------------------------------------------------
 def host_points(n, box, seed):
-    rng = np.random.RandomState(seed)
+    """Rows [0, n) of the GPU arm's rank-0 input: the device generator's Philox stream restated in NumPy
+    (oracle/np_oracle.philox_cube_random), rounded to float32 as the device buffer is, widened to the float64 the
+    C restatement computes in -- the same numbers the kernel reads."""
+    from oracle import np_oracle
     ln, st = box
-    return rng.rand(n, 3) * np.array(ln) + np.array(st)
+    return np_oracle.philox_cube_random(n, ln, st, seed, dtype=np.float32).astype(np.float64)
 
 
 def cpu_fabrik_rate(sample_rows, box, seed=1234, repeats=1):
@@ -153,7 +156,8 @@ def run_reference_arm(args, rank):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic", "gpu_launches": 0,
         "config": {"workload": WORKLOAD, "rows_per_step": sample, "mean_iterations": iters,
-                   "input": "float64 [n,3] host array (NumPy RandomState 1234: the bounded CPU sample of the same box)",
+                   "input": "rows [0, rows_per_step) of the GPU arm's rank-0 input (the same Philox4x32-10 stream, seed 1234, "
+                            "restated in NumPy: float32 values widened to float64)",
                    "fabrik_precision": "fp64 (C restatement of the reference's Python floats)"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
                          "sample": f"{sample} targets per step x {args.steps} steps, oracle/ik_oracle.c "
@@ -716,7 +720,7 @@ def main():
         sample, threads = calibrated_cpu_sample(WORKSPACE_BOX)
         rate, threads, mean_it = cpu_fabrik_rate(sample, WORKSPACE_BOX)
         cpu_baseline = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
-                        "sample": f"{sample} cube_random full-workspace targets (mean {mean_it:.1f} iterations), "
+                        "sample": f"the first {sample} rows of this run's rank-0 input (mean {mean_it:.1f} iterations), "
                                   f"oracle/ik_oracle.c = C restatement of fabrik.py/inverse.py with OpenMP on all host "
                                   f"threads; the pure-Python reference runs ~4e2 solves/s/core on this workload "
                                   f"(BASELINE.md) and does not exist on the GPU box"}

@@ -47,7 +47,9 @@ extern "C" {
 #define IKB_F32 0
 #define IKB_F64 1
 
-/* FABRIK iterate precision (angle extraction is always fp64, reference inverse.py:54-112).     */
+/* FABRIK iterate precision.  The angle extraction (reference inverse.py:54-112) forms its cosines and their 8-decimal
+ * rounding in fp64 either way; what follows the rounding (acos / atan2 and the combination with pi) is evaluated in the
+ * precision of the caller's angle buffer: IKB_F64 buffers <= 1e-9 rad from the reference, IKB_F32 buffers <= 1e-6 rad. */
 #define IKB_FABRIK_F64 0 /* default: fp64 iterate, agrees with the reference to ~1e-12 rad       */
 #define IKB_FABRIK_F32 1 /* fast: fp32 iterate; ~0.4 % of uniform-workspace targets leave the    */
                          /* 1e-4 rad band (convergence-test flips), see DESIGN.md                */
@@ -133,6 +135,8 @@ int ikb_fabrik_calculate_host(ikb_engine *e, const double *init, int64_t n_init,
                               int32_t *iters_out /* nullable */, ikb_stats *stats);
 
 /* ---- forward kinematics (forward.py:73-94) ---------------------------------------------------
+ * (fp32 buffers + err_out only + an arm whose joints 2..4 have alpha = 0 take the HBM-speed kernels of csrc/fk.cu;
+ *  everything else the generic one -- same arithmetic, errors agree to 2e-6)
  * angles n x 4 -> end-effector position n x 3 (column 3 of the last cumulative DH matrix, as read
  * at cli.py:60 / inverse.py:130) and/or position error ||pos - target||.  pos_out, targets and
  * err_out are nullable (err_out needs targets); pos/err use angles_dtype, targets use xyz_dtype. */

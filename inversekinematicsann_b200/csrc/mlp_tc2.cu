@@ -8,9 +8,11 @@
 //     (TS mode, no smem reads at all); only x_lo (fp16) stays in shared memory (128 KB, K-major, 128B swizzle);
 //   * weights are the B operand, N = 256 features per UMMA, tiles of 256 features x 64 k (32 KB) pre-swizzled
 //     on the host and streamed by the TMA engine through a 3-stage ring;
-//   * three products per k step: x_hi w_hi (TS), x_lo w_hi (SS), x_hi w_lo (TS), all into ONE fp32 accumulator
-//     D[128 lanes x 256 columns] per N half.  x is stored times 2^6 so that x_lo stays a normal fp16 number while
-//     sharing the accumulator with x_hi; the factor is folded into the per-layer output scale.
+//   * three products: x_hi w_hi (TS), x_lo w_hi (SS), x_hi w_lo (TS), all into ONE fp32 accumulator
+//     D[128 lanes x 256 columns] per N half -- the two small products for every k chunk FIRST, the main product last
+//     (IKB_TS_CORR_FIRST: the accumulator is truncated toward zero at every K = 16 step, and only steps taken at the
+//     sum's full size cost accuracy).  x is stored times 2^6 so that x_lo stays a normal fp16 number while sharing the
+//     accumulator with x_hi; the factor is folded into the per-layer output scale.
 // TMEM: columns [0, 256) = x_hi, [256, 512) = D.  Per layer: MMA(half 0) -> epilogue drains D into registers ->
 // MMA(half 1) runs while the epilogue turns half 0 into the next layer's activations (kept packed in registers
 // until the issuer's tcgen05.commit says the old activations are dead) -> store (tcgen05.st for x_hi, st.shared

@@ -152,3 +152,43 @@ def fabrik_ikine_np(xyz, links=(2.0, 2.0, 2.0, 2.0), tol=1e-3, max_iter=100,
         mid = _pb(C, E, ce / 2)
         th4 = np.where(bd > _dist(B, mid), -(np.pi - a4), np.pi - a4)
     return np.stack([th1, th2, th3, th4], axis=1), iters
+
+
+# ---- the benchmark's input stream, restated ------------------------------------------------------
+# csrc/generators.cu draws cube_random / random_dist targets from a counter-based Philox4x32-10 stream keyed by
+# (seed, row): 128 bits for counter 2*row (x, y) and 2*row + 1 (z).  The same stream in NumPy, so that the CPU arm of
+# bench.py solves the very rows the GPU arm solves (pinned bit-exact against the device generator by
+# tests/test_wire_and_generators.py::test_philox_stream_matches_the_numpy_restatement).
+
+def _philox4x32_10(seed, ctr):
+    """seed: python int (64 bit); ctr: uint64 array -> four uint32 arrays."""
+    m0, m1 = np.uint64(0xD2511F53), np.uint64(0xCD9E8D57)
+    mask = np.uint64(0xFFFFFFFF)
+    c0, c1 = ctr & mask, ctr >> np.uint64(32)
+    c2 = np.full_like(c0, 0x1BD11BDA)
+    c3 = np.full_like(c0, 0x5851F42D)
+    k0, k1 = int(seed) & 0xFFFFFFFF, (int(seed) >> 32) & 0xFFFFFFFF
+    for _ in range(10):
+        p0, p1 = m0 * c0, m1 * c2                      # 32 x 32 -> 64 bit products
+        hi0, lo0, hi1, lo1 = p0 >> np.uint64(32), p0 & mask, p1 >> np.uint64(32), p1 & mask
+        c0, c1, c2, c3 = hi1 ^ c1 ^ np.uint64(k0), lo1, hi0 ^ c3 ^ np.uint64(k1), lo0
+        k0, k1 = (k0 + 0x9E3779B9) & 0xFFFFFFFF, (k1 + 0xBB67AE85) & 0xFFFFFFFF
+    return c0, c1, c2, c3
+
+
+def _u53(a, b):
+    return (((a >> np.uint64(5)) << np.uint64(26)) | (b >> np.uint64(6))).astype(np.float64) * (1.0 / 9007199254740992.0)
+
+
+def philox_cube_random(n, lens, start, seed, row_offset=0, dtype=np.float64, chunk=1 << 22):
+    """Rows [row_offset, row_offset + n) of TrainingDataGenerator.cube_random_device(..., seed=seed): start + len * U[0,1)
+    per axis (position_generator.py:48-55) with the device generator's Philox stream."""
+    out = np.empty((int(n), 3), dtype=dtype)
+    for lo in range(0, int(n), chunk):
+        hi = min(int(n), lo + chunk)
+        g = np.arange(row_offset + lo, row_offset + hi, dtype=np.uint64)
+        r0, r1, r2, r3 = _philox4x32_10(seed, np.uint64(2) * g)
+        s0, s1, _, _ = _philox4x32_10(seed, np.uint64(2) * g + np.uint64(1))
+        u = np.stack([_u53(r0, r1), _u53(r2, r3), _u53(s0, s1)], axis=1)
+        out[lo:hi] = (u * np.asarray(lens, dtype=np.float64) + np.asarray(start, dtype=np.float64)).astype(dtype)
+    return out

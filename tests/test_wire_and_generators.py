@@ -129,3 +129,19 @@ def test_random_generators_distributions():
         ref = stats.truncnorm(lo / 0.5, hi / 0.5, loc=0, scale=0.5)
         assert stats.kstest(nrm[:50_000, ax], ref.cdf).pvalue > 1e-3
     assert len(G.random_distribution(100, lim, "normal", 0.35)) == 100
+
+
+@pytest.mark.gpu
+def test_philox_stream_matches_the_numpy_restatement():
+    """The device generator's cube_random stream (Philox4x32-10 keyed by seed and row) against its NumPy restatement,
+    bit for bit, float64 and float32, with a row offset: bench.py's CPU arm solves rows of this stream."""
+    from inversekinematicsann_b200.robot import position_generator as pg
+    from oracle import np_oracle
+    lens, start = (6.0, 12.0, 9.0), (0.0, -6.0, -3.0)
+    for dtype in ("float64", "float32"):
+        dev = pg._generate(pg.GEN_CUBE_RANDOM, list(lens) + list(start), 100_003, dtype=dtype, seed=1234,
+                           row_offset=7).cpu().numpy()
+        host = np_oracle.philox_cube_random(100_003, lens, start, 1234, row_offset=7, dtype=np.dtype(dtype))
+        assert np.array_equal(dev, host), dtype
+    other = np_oracle.philox_cube_random(1000, lens, start, 1235)
+    assert not np.array_equal(other, np_oracle.philox_cube_random(1000, lens, start, 1234))
