@@ -186,7 +186,7 @@ def main():
     from inversekinematicsann_b200.engine import fabrik_algorithmic_flops
     from inversekinematicsann_b200.kinematics.inverse import AnnInverseKinematics, FabrikInverseKinematics
     from inversekinematicsann_b200.robot.robot import SixDOFRobot as R
-    from inversekinematicsann_b200.sharding import ShardedFabrik, gather_rows, reduce_stats
+    from inversekinematicsann_b200.sharding import PeerGather, ShardedFabrik, gather_rows, reduce_stats
 
     def bind_to_gpu_numa_node(index):
         """Pin this rank to the CPUs next to its GPU so that its pinned staging buffers are allocated on the
@@ -209,7 +209,8 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        from datetime import timedelta
+        dist.init_process_group("nccl", device_id=dev, timeout=timedelta(seconds=180))   # a hang fails fast
 
     def barrier():
         if world > 1:
@@ -429,7 +430,7 @@ def main():
         only_secs, _, _ = timed_device_loop(lambda: gather_rows(angles, n_total, dst=0, out=full), g_steps, 2)
         both_secs, _, _ = timed_device_loop(
             lambda: sh.ikine_device(xyz, angles, n_total=n_total, gather_dst=0, gather_out=full, check=False,
-                                    chunk_rows=GATHER_CHUNK), g_steps, 2)
+                                    chunk_rows=GATHER_CHUNK, gather_mode="nccl"), g_steps, 2)
         # every shard must have landed at its own rows of rank 0's buffer
         probe = torch.zeros(world, dtype=torch.float64, device=dev)
         probe[rank] = angles[:4096].double().sum() + angles[-4096:].double().sum()
@@ -439,12 +440,34 @@ def main():
             got = torch.stack([full[r * n: r * n + 4096].double().sum() + full[(r + 1) * n - 4096: (r + 1) * n].double().sum()
                                for r in range(world)])
             order_ok = bool(torch.equal(got, probe))
+        # the same with copy-engine pushes into rank 0's buffer (symmetric memory): no NCCL kernels next to K1
+        peer = None
+        try:
+            pg = PeerGather(n_total, 4, torch.float32, dev, dst=0)
+            p2p_secs, _, _ = timed_device_loop(
+                lambda: sh.ikine_device(xyz, angles, n_total=n_total, gather_dst=0, check=False, chunk_rows=GATHER_CHUNK,
+                                        peer_gather=pg), g_steps, 2)
+            probe2 = torch.zeros(world, dtype=torch.float64, device=dev)
+            probe2[rank] = angles[:4096].double().sum() + angles[-4096:].double().sum()
+            dist.all_reduce(probe2, op=dist.ReduceOp.SUM)
+            ok2 = None
+            if rank == 0:
+                got2 = torch.stack([pg.buf[r * n: r * n + 4096].double().sum() + pg.buf[(r + 1) * n - 4096: (r + 1) * n].double().sum()
+                                    for r in range(world)])
+                ok2 = bool(torch.equal(got2, probe2))
+            peer = {"overlapped_ms": p2p_secs / g_steps * 1e3,
+                    "solve_plus_gather_over_solve": (p2p_secs / g_steps) / (secs / args.steps), "order_verified": ok2,
+                    "how": "PeerGather: finished 16 Mi-row chunks pushed into rank 0's buffer (torch symmetric memory mapped "
+                           "over NVLink) with device-to-device copies on a side stream -- copy engines, no SMs"}
+            del pg
+        except Exception as exc:   # symmetric memory unavailable on this box / torch build
+            peer = {"unavailable": f"{type(exc).__name__}: {exc}"[:300]}
         moved = (world - 1) * n * 16
         gather = {"rows_total": n_total, "dst": 0, "bytes_into_dst": moved,
                   "ms": only_secs / g_steps * 1e3, "GBps_into_dst": moved / (only_secs / g_steps) / 1e9,
                   "solve_ms": secs / args.steps * 1e3, "overlapped_ms": both_secs / g_steps * 1e3,
                   "solve_plus_gather_over_solve": (both_secs / g_steps) / (secs / args.steps),
-                  "order_verified": order_ok,
+                  "order_verified": order_ok, "copy_engine_push": peer,
                   "chunk_rows": GATHER_CHUNK,
                   "how": "ShardedFabrik.ikine_device: K1 per 16 Mi-row chunk, finished chunks shipped to rank 0 with NCCL "
                          "send/recv (point-to-point, received in place) while the next chunk is solved; `ms` is the "

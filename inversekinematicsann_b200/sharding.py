@@ -81,6 +81,40 @@ def gather_rows(local_rows, n_total, dst=0, out=None):
     return full
 
 
+class PeerGather:
+    """The final gather without NCCL kernels: every rank maps rank `dst`'s result buffer into its own address space
+    (torch symmetric memory over NVLink / NVSwitch peer access) and pushes each finished chunk of its shard there with a
+    device-to-device copy on a side stream -- copy-engine DMA, no SMs, so it overlaps the solve of the next chunk
+    without competing with it.  `finish()` makes the launching stream wait for the pushes and runs a device-side
+    barrier across the ranks; after it `result` (on `dst`) holds all n_total rows in trajectory order.
+    Needs an NCCL process group on one NVLink-connected node; construction raises where symmetric memory is
+    unavailable and the caller falls back to send/recv (`gather_rows`)."""
+
+    def __init__(self, n_total, cols, dtype, device, dst=0):
+        import torch.distributed._symmetric_memory as symm
+        self.dst, self.n_total = dst, int(n_total)
+        group = dist.group.WORLD
+        self.buf = symm.empty((self.n_total, cols), dtype=dtype, device=device)   # same size on every rank
+        self.hdl = symm.rendezvous(self.buf, group)
+        self.dst_view = self.hdl.get_buffer(dst, (self.n_total, cols), dtype)
+        self.stream = torch.cuda.Stream(device)
+        self.rank = dist.get_rank()
+
+    def push(self, rows, first_row):
+        """Copy `rows` (this rank's finished chunk, produced on the current stream) to rows
+        [first_row, first_row + len) of dst's buffer, asynchronously on the side stream."""
+        done = torch.cuda.Event()
+        done.record()
+        self.stream.wait_event(done)
+        with torch.cuda.stream(self.stream):
+            self.dst_view[first_row: first_row + rows.shape[0]].copy_(rows, non_blocking=True)
+
+    def finish(self):
+        torch.cuda.current_stream().wait_stream(self.stream)
+        self.hdl.barrier()                      # every rank's pushes have been issued and completed on its streams
+        return self.buf if self.rank == self.dst else None
+
+
 def chunk_ranges(n, chunk_rows):
     """[lo, hi) pieces of a shard of n rows, the grid both ends of the chunked gather agree on."""
     return [(lo, min(lo + chunk_rows, n)) for lo in range(0, n, chunk_rows)]
@@ -132,12 +166,17 @@ class _ShardedIkine:
         return None if full is None else full.cpu().numpy()
 
     def ikine_device(self, xyz_shard, out_shard=None, n_total=None, gather_dst=None, gather_out=None,
-                     chunk_rows=1 << 24, fk_error=False, check=True):
+                     chunk_rows=1 << 24, fk_error=False, check=True, peer_gather=None, gather_mode="auto"):
         """Solve this rank's rows where they are.  xyz_shard: (n_local, 3) CUDA tensor = rows
         shard_range(n_total, rank, world) of the trajectory; out_shard: optional (n_local, 4) CUDA tensor.
         Returns out_shard, or -- with gather_dst -- the full (n_total, 4) tensor on that rank and None elsewhere.
         `check=False` skips the diagnostics round trip (one device->host read + one all-reduce): the caller vouches
-        for the inputs and reads `eng.stats_fetch_torch()` itself."""
+        for the inputs and reads `eng.stats_fetch_torch()` itself.
+        The gather ships finished chunks while the next one is solved: with copy-engine pushes into dst's mapped buffer
+        (PeerGather; `gather_mode` "auto" uses it when torch symmetric memory works on every rank, "p2p" insists,
+        "nccl" never does; a PeerGather may also be passed in as `peer_gather`) or with NCCL send/recv.  Every rank must
+        pass the same `gather_mode`.  With PeerGather the result on dst is its symmetric buffer, valid until the next
+        gather of the same size; `gather_out` (a preallocated result on dst) applies to the NCCL transport only."""
         world, rank = self._world_rank()
         eng = self._engine()
         n_local = int(xyz_shard.shape[0])
@@ -153,6 +192,20 @@ class _ShardedIkine:
         if check:
             eng.stats_reset_torch()
         gathering = gather_dst is not None and world > 1
+        # NOTE: which transport is used must not depend on anything rank-local (e.g. `gather_out`, which only dst
+        # passes): every rank has to take the same branch or the job deadlocks.
+        if gathering and peer_gather is None and gather_mode in ("auto", "p2p"):
+            peer_gather = self._peer_gather(n_total, out_shard, gather_dst, insist=gather_mode == "p2p")
+        if gathering and peer_gather is not None:
+            for a, b in chunk_ranges(n_local, chunk_rows):
+                self._solve_device(eng, xyz_shard[a:b], out_shard[a:b], fk_error)
+                peer_gather.push(out_shard[a:b], lo + a)
+            full = peer_gather.finish()
+            if check:
+                total = reduce_stats(eng.stats_fetch_torch(), row_offset=lo)
+                self.ik.last_stats = total
+                self.ik._raise_from_stats(_RowPrinter(xyz_shard, lo), total)
+            return full
         full, pending = None, []
         if gathering and rank == gather_dst:
             full = gather_out if gather_out is not None else \
@@ -188,6 +241,29 @@ class _ShardedIkine:
             return full
         return out_shard
 
+
+    _PEER_GATHERS = {}
+
+    @classmethod
+    def _peer_gather(cls, n_total, out_shard, dst, insist=False):
+        """One cached PeerGather per (rows, dtype, device, dst); None where symmetric memory is not available (decided by
+        all ranks together, so that nobody is left waiting in a rendezvous)."""
+        if not out_shard.is_cuda or dist.get_backend() != "nccl":
+            if insist:
+                raise RuntimeError("gather_mode='p2p' needs CUDA tensors and an NCCL process group")
+            return None
+        key = (int(n_total), str(out_shard.dtype), out_shard.device.index, int(dst))
+        if key not in cls._PEER_GATHERS:
+            try:
+                made = PeerGather(n_total, out_shard.shape[1], out_shard.dtype, out_shard.device, dst=dst)
+            except Exception:
+                if insist:
+                    raise
+                made = None
+            ok = torch.tensor([1 if made is not None else 0], device=out_shard.device)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            cls._PEER_GATHERS[key] = made if int(ok.item()) == 1 else None
+        return cls._PEER_GATHERS[key]
 
     def ikine_from_root(self, points=None, root=0, out=None):
         """One request that arrives on ONE rank (the broker of rpc_broker.py:76-100), served by all GPUs: `root` pushes

@@ -97,3 +97,29 @@ def test_two_rank_sharded_ann_with_fk_round_trip(tmp_path):
     assert np.array_equal(single, np.load(tmp_path / "ann.npy"))
     s, c = np.load(tmp_path / "ann_fk.npy")
     assert c == 20_003 and abs(s / c - float(np.mean(err, dtype=np.float64))) <= 1e-6
+
+
+def test_device_resident_form_in_one_process():
+    """ShardedFabrik.ikine_device / ikine_from_root without a process group are a world of one: the rows stay in HBM,
+    the reference's exceptions are raised from the device-side diagnostics, and the numbers equal ikine()'s.
+    (The multi-rank gather is exercised with NCCL by bench.py at N > 1, which verifies the row order of the result, and
+    with gloo on CPU tensors in tests/test_sharding_gloo.py.)"""
+    import torch
+    from inversekinematicsann_b200.kinematics.inverse import FabrikInverseKinematics
+    from inversekinematicsann_b200.robot.robot import OutOfRobotReachException, SixDOFRobot as R
+    from inversekinematicsann_b200.sharding import ShardedFabrik
+    ik = FabrikInverseKinematics(R.dh_matrix, R.links_lengths, R.effector_workspace_limits)
+    rng = np.random.RandomState(29)
+    pts = (rng.rand(50_001, 3) * [6, 12, 9] + [0, -6, -3]).astype(np.float32)
+    want = ik.ikine(pts, out=np.empty((len(pts), 4), np.float32))
+    sh = ShardedFabrik(ik)
+    got = sh.ikine_device(torch.from_numpy(pts).cuda(), n_total=len(pts), gather_dst=0, chunk_rows=16_384)
+    assert got.is_cuda and np.array_equal(got.cpu().numpy(), want, equal_nan=True)
+    assert ik.last_stats.n_solved == len(pts)
+    served = sh.ikine_from_root(pts)
+    assert np.array_equal(served, want, equal_nan=True)
+    bad = pts.copy()
+    bad[40_000, 0] = -0.5
+    with pytest.raises(OutOfRobotReachException) as exc:
+        sh.ikine_device(torch.from_numpy(bad).cuda())
+    assert "-0.5" in str(exc.value)
