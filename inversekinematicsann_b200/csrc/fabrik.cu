@@ -346,7 +346,10 @@ __device__ __noinline__ double fused_fk_error_f64(double t0, double t1, double t
 // theta_1 of the target's plane, the x == 0 flag): no second read of the input (round 1 re-read the row here).
 // CONST_LINKS: the chain was iterated in fp64, so its segments have their link lengths to the last place (see below);
 // an fp32-iterated chain is only good to 1e-7 there and takes the general form with computed lengths.
-template <bool FUSE_FK, bool OUT32, bool CONST_LINKS, typename Th1>
+// ZERO_ITER: the reference's loop never runs (tol >= 1 or max_iter <= 0) and every chain is the seed chain -- a separate
+// instantiation, so that the common one carries none of its code (the seed constants alone were 18 instructions per
+// extraction when this was a run-time branch).
+template <bool FUSE_FK, bool OUT32, bool CONST_LINKS, bool ZERO_ITER, typename Th1>
 __device__ __forceinline__ void fabrik_epilogue(const FabrikArgs &a, int idx, int k_raw, double r1, double z1, double r2,
                                                 double z2, double Tr, double Tz, Th1 th1, double &fk_sum, unsigned &fk_cnt)
 {
@@ -358,7 +361,7 @@ __device__ __forceinline__ void fabrik_epilogue(const FabrikArgs &a, int idx, in
     double r3, z3, c2, c3, c4, n_bd, n_ce;
     bool odd;  // anything that needs the slow classification below: a cosine outside [-1, 1], NaN, a zero length
     double n2 = 1.0;
-    if (!rc.zero_iter) {  // f3 = PB(f2, T, d3) (fabrik.py:40)
+    if (!ZERO_ITER) {  // f3 = PB(f2, T, d3) (fabrik.py:40)
         const double dr = Tr - r2, dz = Tz - z2;
         n2 = fma(dz, dz, dr * dr);
         const double s = ikb_rsqrt_times(n2, rc.link_k[3]);
@@ -367,7 +370,7 @@ __device__ __forceinline__ void fabrik_epilogue(const FabrikArgs &a, int idx, in
         r1 = rc.seed_r[1]; z1 = rc.seed_z[1]; r2 = rc.seed_r[2]; z2 = rc.seed_z[2];
         r3 = rc.seed_r[3]; z3 = rc.seed_z[3];
     }
-    if (CONST_LINKS && !rc.zero_iter) {
+    if (CONST_LINKS && !ZERO_ITER) {
         // The three cosines of inverse.py:77-100 on squared lengths.  After at least one pass B = S and C, D, E are
         // points at distance d1, d2, d3 from their predecessor (f1 = PB(S, b1, d1) etc.), so |BC|, |CD|, |DE| ARE the
         // link lengths up to the last-place rounding the reference's own sqrt / division carry -- the same order as
@@ -519,7 +522,7 @@ struct WarpQueues {
 //     exactly max_iter passes without verdict, vote or parking, while the warp's reachable chains wait in registers.
 // The input rows of the NEXT staging step are loaded before the pass loop and consumed after it (their latency is
 // hidden behind the passes).
-template <typename Real, bool FUSE_FK, bool OUT32>
+template <typename Real, bool FUSE_FK, bool OUT32, bool ZERO_ITER>
 __device__ __forceinline__ void fabrik_warp_loop(const FabrikArgs &a, WarpQueues<Real, typename TailType<OUT32>::type> *s_queues)
 {
     using Th1 = typename TailType<OUT32>::type;
@@ -532,7 +535,7 @@ __device__ __forceinline__ void fabrik_warp_loop(const FabrikArgs &a, WarpQueues
     const LinkScale<Real> d1(rc.link_k[1]), d2(rc.link_k[2]);
     const Band<Real> start_band = make_band<Real>(rc, 0), goal_band = make_band<Real>(rc, 1);
     const int max_iter = rc.max_iter;
-    const bool zero_iter = rc.zero_iter != 0;
+    constexpr bool zero_iter = ZERO_ITER;
 
     // lane-refill state: one chain per lane
     bool active = false;
@@ -618,7 +621,7 @@ __device__ __forceinline__ void fabrik_warp_loop(const FabrikArgs &a, WarpQueues
                 const int2 ik = q.out_ik[slot];
                 const int k_raw = ik.y;
                 const Real2 j1 = q.out_j1[slot], j2 = q.out_j2[slot], tt = q.out_t[slot];
-                fabrik_epilogue<FUSE_FK, OUT32, sizeof(Real) == 8, Th1>(a, ik.x, k_raw, (double)j1.x, (double)j1.y,
+                fabrik_epilogue<FUSE_FK, OUT32, sizeof(Real) == 8, ZERO_ITER, Th1>(a, ik.x, k_raw, (double)j1.x, (double)j1.y,
                                                                         (double)j2.x, (double)j2.y, (double)tt.x,
                                                                         (double)tt.y, q.out_th1[slot], fk_sum, fk_cnt);
                 iters_local += (unsigned)(k_raw & IKB_K_MASK);
@@ -798,11 +801,11 @@ __device__ __forceinline__ void fabrik_warp_loop(const FabrikArgs &a, WarpQueues
     }
 }
 
-template <typename Real, bool FUSE_FK, bool OUT32>
+template <typename Real, bool FUSE_FK, bool OUT32, bool ZERO_ITER>
 __global__ void __launch_bounds__(IKB_FABRIK_WARPS * 32, IKB_FABRIK_MIN_CTAS) fabrik_planar_kernel(const FabrikArgs a)
 {
     extern __shared__ __align__(16) unsigned char s_raw[];
-    fabrik_warp_loop<Real, FUSE_FK, OUT32>(a, reinterpret_cast<WarpQueues<Real, typename TailType<OUT32>::type> *>(s_raw));
+    fabrik_warp_loop<Real, FUSE_FK, OUT32, ZERO_ITER>(a, reinterpret_cast<WarpQueues<Real, typename TailType<OUT32>::type> *>(s_raw));
 }
 
 // ---- generic 3-D path ---------------------------------------------------------------------------
@@ -992,22 +995,28 @@ __global__ void __launch_bounds__(128) fabrik_generic_ikine_kernel(const FabrikG
 
 // ---- launchers (called from capi.cu) --------------------------------------------------------------
 namespace {
-template <typename Real, bool FUSE_FK, bool OUT32>
-cudaError_t launch_planar(const FabrikArgs &a, unsigned grid, cudaStream_t stream)
+template <typename Real, bool FUSE_FK, bool OUT32, bool ZERO_ITER>
+cudaError_t launch_planar_z(const FabrikArgs &a, unsigned grid, cudaStream_t stream)
 {
     constexpr size_t smem = sizeof(WarpQueues<Real, typename TailType<OUT32>::type>) * IKB_FABRIK_WARPS;
-    static const cudaError_t attr = cudaFuncSetAttribute(fabrik_planar_kernel<Real, FUSE_FK, OUT32>,
+    static const cudaError_t attr = cudaFuncSetAttribute(fabrik_planar_kernel<Real, FUSE_FK, OUT32, ZERO_ITER>,
                                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (attr != cudaSuccess)
         return attr;
     // three CTAs per SM need ~200 KB of shared memory: ask for the largest carve-out
-    static const cudaError_t carve = cudaFuncSetAttribute(fabrik_planar_kernel<Real, FUSE_FK, OUT32>,
+    static const cudaError_t carve = cudaFuncSetAttribute(fabrik_planar_kernel<Real, FUSE_FK, OUT32, ZERO_ITER>,
                                                           cudaFuncAttributePreferredSharedMemoryCarveout,
                                                           (int)cudaSharedmemCarveoutMaxShared);
     if (carve != cudaSuccess)
         return carve;
-    fabrik_planar_kernel<Real, FUSE_FK, OUT32><<<grid, IKB_FABRIK_WARPS * 32, smem, stream>>>(a);
+    fabrik_planar_kernel<Real, FUSE_FK, OUT32, ZERO_ITER><<<grid, IKB_FABRIK_WARPS * 32, smem, stream>>>(a);
     return cudaGetLastError();
+}
+template <typename Real, bool FUSE_FK, bool OUT32>
+cudaError_t launch_planar(const FabrikArgs &a, unsigned grid, cudaStream_t stream)
+{
+    return a.rc.zero_iter ? launch_planar_z<Real, FUSE_FK, OUT32, true>(a, grid, stream)
+                          : launch_planar_z<Real, FUSE_FK, OUT32, false>(a, grid, stream);
 }
 }  // namespace
 
