@@ -130,8 +130,10 @@ class _ShardedIkine:
     (BASELINE config 4: the FK round trip of every prediction), available as `ik.last_stats.mean_fk_error`.
 
     `ikine_device(xyz_shard, ...)`: the device-resident form -- each rank holds only ITS rows in HBM, nothing
-    touches the host, and the optional gather ships finished chunks to `gather_dst` over NCCL send/recv while the
-    next chunk is being solved."""
+    touches the host, and the optional gather ships finished chunks to `gather_dst` while the next chunk is being
+    solved (copy-engine pushes over NVLink where torch symmetric memory works, else NCCL send/recv).
+
+    `ikine_from_root(points)`: one request that arrives on one rank, served by all GPUs."""
 
     def __init__(self, ik):
         self.ik = ik
@@ -240,7 +242,6 @@ class _ShardedIkine:
         if gathering:
             return full
         return out_shard
-
 
     _PEER_GATHERS = {}
 
