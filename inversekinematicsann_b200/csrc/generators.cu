@@ -79,8 +79,8 @@ __global__ void __launch_bounds__(256) generate_kernel(const GenArgs a)
             philox4x32(a.seed, 2ULL * (unsigned long long)g + 1, r2);
             const double u0 = u53(r[0], r[1]), u1 = u53(r[2], r[3]), u2 = u53(r2[0], r2[1]);
             if (a.kind == IKB_GEN_CUBE_RANDOM) { // :48-55: start + len * U[0,1) per axis
-                // separately rounded product and sum (no FMA contraction): the stream is restated bit for bit in
-                // oracle/np_oracle.philox_cube_random, which is how the CPU arm of bench.py gets the same rows
+                // separately rounded product and sum (no FMA contraction): the stream is restated bit for bit in NumPy
+                // by the test infrastructure, which is how the CPU arm of bench.py gets the same rows
                 x = __dadd_rn(__dmul_rn(u0, a.p[0]), a.p[3]);
                 y = __dadd_rn(__dmul_rn(u1, a.p[1]), a.p[4]);
                 z = __dadd_rn(__dmul_rn(u2, a.p[2]), a.p[5]);
