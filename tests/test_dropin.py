@@ -4,7 +4,8 @@ CPU: with dropin/ ahead of the reference tree every `kinematics.*` / `robot.*` i
 the reference's tests resolves to the shims while the reference's own `tests`, `plot`, `cli`, `rpc_broker` stay its
 own, and `cli.CLI()` constructs.  GPU: the reference's unit suites, cli.py and the broker callback run unmodified
 (tools/run_reference_suite.py).  Both need a checkout of the reference (IK_REFERENCE_ROOT, /root/reference, or
-the untracked .refscratch/ copy that travels to the GPU box)."""
+an untracked .refscratch/ copy placed there for one run on the GPU box, which has no /root/reference: that run's log is
+profiles/r02_dropin_suite.log); without one the tests skip."""
 import os
 import subprocess
 import sys
