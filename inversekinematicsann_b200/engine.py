@@ -183,7 +183,7 @@ class IkEngine:
         iters = np.empty(n, dtype=np.int32) if return_iters else None
         fk_err = np.empty(n, dtype=out.dtype) if return_fk_error else None
         s = _native.IkbStats()
-        prec = {"f64": _native.IKB_FABRIK_F64, "f32": _native.IKB_FABRIK_F32}[precision]
+        prec = _choice(_FABRIK_PRECISIONS, precision, "precision")
         self._check(self._lib.ikb_fabrik_solve_host(
             self._handle, xyz.ctypes.data, _np_dtype_code(xyz), n, out.ctypes.data, _np_dtype_code(out),
             iters.ctypes.data if return_iters else None, fk_err.ctypes.data if return_fk_error else None,
@@ -265,6 +265,7 @@ class IkEngine:
 
     def ann_solve(self, xyz, out=None, mode="fp32", return_fk_error=False, fk_stats=False):
         """reference ann.py:70-76 on an (n, 3) array -> (angles float32 [n,4], stats[, fk_error float32 [n]])."""
+        mode_code = _choice(_MLP_MODES, mode, "mode")
         xyz = self._rows(xyz, 3, "points")
         n = xyz.shape[0]
         if out is None:
@@ -274,7 +275,7 @@ class IkEngine:
         s = _native.IkbStats()
         self._check(self._lib.ikb_ann_solve_host(self._handle, xyz.ctypes.data, _np_dtype_code(xyz), n,
                                                  out.ctypes.data, fk_err.ctypes.data if return_fk_error else None,
-                                                 int(bool(fk_stats)), _MLP_MODES[mode], ctypes.byref(s)),
+                                                 int(bool(fk_stats)), mode_code, ctypes.byref(s)),
                     "ikb_ann_solve_host")
         return (out, IkStats.from_c(s), fk_err) if return_fk_error else (out, IkStats.from_c(s))
 
@@ -345,7 +346,7 @@ class IkEngine:
             self._dev_vec(iters, xyz.shape[0], "torch.int32", "iters")
         if fk_err is not None:
             self._dev_vec(fk_err, xyz.shape[0], str(out.dtype), "fk_err")
-        prec = {"f64": _native.IKB_FABRIK_F64, "f32": _native.IKB_FABRIK_F32}[precision]
+        prec = _choice(_FABRIK_PRECISIONS, precision, "precision")
         self._check(self._lib.ikb_fabrik_solve_device(
             self._handle, xyz.data_ptr(), _torch_dtype_code(xyz), xyz.shape[0], out.data_ptr(),
             _torch_dtype_code(out), iters.data_ptr() if iters is not None else None,
@@ -353,6 +354,7 @@ class IkEngine:
             _torch_stream_ptr(self.device)), "ikb_fabrik_solve_device")
 
     def ann_solve_device(self, xyz, out, mode="fp32", fk_err=None, fk_stats=False):
+        mode_code = _choice(_MLP_MODES, mode, "mode")
         xyz = self._dev_rows(xyz, 3, "points")
         out = self._dev_rows(out, 4, "angles")
         self._same_rows(xyz, out, "angles")
@@ -363,7 +365,7 @@ class IkEngine:
         self._check(self._lib.ikb_ann_solve_device(
             self._handle, xyz.data_ptr(), _torch_dtype_code(xyz), xyz.shape[0], out.data_ptr(),
             fk_err.data_ptr() if fk_err is not None else None, int(bool(fk_stats)),
-            _MLP_MODES[mode], _torch_stream_ptr(self.device)), "ikb_ann_solve_device")
+            mode_code, _torch_stream_ptr(self.device)), "ikb_ann_solve_device")
 
     def fk_device(self, angles, targets=None, pos=None, err=None):
         angles = self._dev_rows(angles, 4, "angles")
@@ -436,6 +438,14 @@ class PinnedBuffer:
 
 _MLP_MODES = {"fp32": _native.IKB_MLP_FP32_SIMT, "fp16x3": _native.IKB_MLP_FP16X3_TC,
               "fp16x3_ts": _native.IKB_MLP_FP16X3_TS}
+_FABRIK_PRECISIONS = {"f64": _native.IKB_FABRIK_F64, "f32": _native.IKB_FABRIK_F32}
+
+
+def _choice(table, key, what):
+    try:
+        return table[key]
+    except (KeyError, TypeError):
+        raise ValueError(f"{what} must be one of {sorted(table)}, got {key!r}") from None
 
 # algorithmic work per unit (SURVEY 8d / DESIGN.md), used by bench.py's roofline arithmetic
 FABRIK_FLOPS_PER_ITERATION = 114

@@ -148,6 +148,12 @@ class _ShardedIkine:
     def _world_rank():
         return (dist.get_world_size(), dist.get_rank()) if _dist_ready() else (1, 0)
 
+    @staticmethod
+    def _collective_device(eng):
+        """Where the tensors of the collectives live: the ENGINE's GPU under NCCL (not torch's current device, which
+        the caller may never have set), the host under gloo."""
+        return f"cuda:{eng.device}" if _dist_ready() and dist.get_backend() == "nccl" else "cpu"
+
     def ikine(self, points, gather=True, fk_error=False, dst=0):
         import numpy as np
         from .kinematics._shared import points_to_array
@@ -158,12 +164,12 @@ class _ShardedIkine:
         eng = self._engine()
         angles, stats = self._solve_local(eng, local, fk_error) if hi > lo else \
             (np.zeros((0, 4), dtype=self._out_dtype), IkStats())
-        total = reduce_stats(stats, row_offset=lo)
+        dev = self._collective_device(eng)
+        total = reduce_stats(stats, row_offset=lo, device=dev)
         self.ik.last_stats = total
         self.ik._raise_from_stats(points, total)
         if not gather or world == 1:
             return angles
-        dev = f"cuda:{eng.device}" if dist.get_backend() == "nccl" else "cpu"
         full = gather_rows(torch.from_numpy(angles).to(dev), arr.shape[0], dst=dst)
         return None if full is None else full.cpu().numpy()
 
@@ -177,8 +183,9 @@ class _ShardedIkine:
         The gather ships finished chunks while the next one is solved: with copy-engine pushes into dst's mapped buffer
         (PeerGather; `gather_mode` "auto" uses it when torch symmetric memory works on every rank, "p2p" insists,
         "nccl" never does; a PeerGather may also be passed in as `peer_gather`) or with NCCL send/recv.  Every rank must
-        pass the same `gather_mode`.  With PeerGather the result on dst is its symmetric buffer, valid until the next
-        gather of the same size; `gather_out` (a preallocated result on dst) applies to the NCCL transport only."""
+        pass the same `gather_mode`.  With PeerGather the result on dst is its symmetric buffer, valid until ANY rank
+        starts the next gather of the same size (its pushes land in the same rows; copy the result out, or synchronise
+        the ranks, before that); `gather_out` (a preallocated result on dst) applies to the NCCL transport only."""
         world, rank = self._world_rank()
         eng = self._engine()
         n_local = int(xyz_shard.shape[0])
@@ -204,7 +211,7 @@ class _ShardedIkine:
                 peer_gather.push(out_shard[a:b], lo + a)
             full = peer_gather.finish()
             if check:
-                total = reduce_stats(eng.stats_fetch_torch(), row_offset=lo)
+                total = reduce_stats(eng.stats_fetch_torch(), row_offset=lo, device=xyz_shard.device)
                 self.ik.last_stats = total
                 self.ik._raise_from_stats(_RowPrinter(xyz_shard, lo), total)
             return full
@@ -236,7 +243,7 @@ class _ShardedIkine:
         for work in pending:
             work.wait()
         if check:
-            total = reduce_stats(eng.stats_fetch_torch(), row_offset=lo)
+            total = reduce_stats(eng.stats_fetch_torch(), row_offset=lo, device=xyz_shard.device)
             self.ik.last_stats = total
             self.ik._raise_from_stats(_RowPrinter(xyz_shard, lo), total)
         if gathering:

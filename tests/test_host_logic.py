@@ -119,6 +119,15 @@ def test_out_buffer_validation_happens_before_the_c_abi():
         IkEngine._check_out(ro, 5, 4, (np.float32,), "out")
 
 
+def test_unknown_mode_or_precision_is_a_value_error():
+    from inversekinematicsann_b200 import engine
+    assert engine._choice(engine._MLP_MODES, "fp16x3_ts", "mode") == engine._native.IKB_MLP_FP16X3_TS
+    for table, key, what in ((engine._MLP_MODES, "bf16", "mode"), (engine._FABRIK_PRECISIONS, "f16", "precision"),
+                             (engine._MLP_MODES, ["fp32"], "mode")):
+        with pytest.raises(ValueError, match=what):
+            engine._choice(table, key, what)
+
+
 def test_raise_from_stats_same_row_in_two_error_classes():
     """A zero-division row and a domain-error row with the same index must not break the exception mapping."""
     from inversekinematicsann_b200.engine import IkStats
